@@ -1,0 +1,178 @@
+/*
+ * vc2_b200.h -- C ABI of the B200-native VC-2 picture path (libvc2b200.so).
+ *
+ * This is the drop-in boundary for the data-parallel picture path of
+ * bbc/vc2_conformance.  The reference has no FFI of its own (it is pure
+ * Python); each entry point below replaces the Python function(s) cited next
+ * to it (paths relative to /root/reference/vc2_conformance/), and
+ * INTEGRATION.md shows the ctypes binding a maintainer of the reference adds.
+ *
+ * Conventions
+ *  - every `d_*` pointer is a DEVICE pointer; everything else is host memory;
+ *  - every call only ENQUEUES work on `stream` (a cudaStream_t passed as
+ *    void*) and returns immediately; results are valid after the stream is
+ *    synchronised;
+ *  - return value: 0 on success, VC2B_E_* (<0) for argument errors, or a
+ *    positive cudaError_t from the launch;
+ *  - the library never allocates device memory: callers size buffers with the
+ *    vc2b_*_count / vc2b_*_bytes helpers;
+ *  - a "batch" is `npictures` pictures coded with identical parameters.
+ *
+ * Numeric envelope: the reference computes in unbounded Python integers.  This
+ * library stores coefficients as int32 and reports VC2B_ST_INT32_ENVELOPE (per
+ * picture) if a decoded or dequantised value does not fit, instead of wrapping.
+ */
+#ifndef VC2_B200_H
+#define VC2_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VC2B_MAX_LEVELS 16 /* dwt_depth + dwt_depth_ho + 1 <= 16 */
+#define VC2B_MAX_BANDS 32  /* 1 + dwt_depth_ho + 3*dwt_depth <= 32 */
+
+/* Picture-path parameters: the subset of the reference's `State`
+ * (pseudocode/state.py:22-390) that the picture path reads.
+ * quant_matrix[level][slot]: slot 0 = LL/L (level 0), 1 = HL or H, 2 = LH, 3 = HH
+ * (State["quant_matrix"], pseudocode/state.py:120). */
+typedef struct vc2b_params {
+    int32_t luma_width, luma_height;             /* pseudocode/video_parameters.py:177 */
+    int32_t color_diff_width, color_diff_height;
+    int32_t luma_depth, color_diff_depth;        /* pseudocode/video_parameters.py:202 */
+    int32_t wavelet_index, wavelet_index_ho;     /* decoder/picture_syntax.py:94-173 */
+    int32_t dwt_depth, dwt_depth_ho;
+    int32_t slices_x, slices_y;                  /* decoder/picture_syntax.py:175 */
+    int32_t is_ld;                               /* parse code 0xC8 (1) or 0xE8 (0) */
+    int32_t slice_prefix_bytes, slice_size_scaler; /* HQ */
+    int64_t slice_bytes_numerator, slice_bytes_denominator; /* LD */
+    int32_t quant_matrix[VC2B_MAX_LEVELS][4];
+} vc2b_params;
+
+/* argument errors */
+#define VC2B_E_BAD_PARAMS (-1)
+#define VC2B_E_UNSUPPORTED (-2)
+#define VC2B_E_SCRATCH_TOO_SMALL (-3)
+
+/* per-picture status words written by the unpack kernels (d_status[4*i+0]) */
+#define VC2B_ST_OK 0
+#define VC2B_ST_UNEXPECTED_END_OF_STREAM 1 /* decoder/io.py:197 UnexpectedEndOfStream */
+#define VC2B_ST_INVALID_SLICE_Y_LENGTH 2   /* decoder/transform_data_syntax.py:166 */
+#define VC2B_ST_INT32_ENVELOPE 4           /* value outside the int32 envelope */
+
+/* ---- introspection --------------------------------------------------------------- */
+const char *vc2b_version(void);
+/* Checks a parameter set; 0 if the library supports it. */
+int vc2b_check_params(const vc2b_params *p);
+/* Subband geometry (pseudocode/slice_sizes.py:53-92).  Subbands are numbered in bitstream
+ * order: level 0 (LL or L), H of each horizontal-only level, then HL,LH,HH per 2-D level. */
+int vc2b_num_subbands(const vc2b_params *p);
+int vc2b_subband_info(const vc2b_params *p, int comp, int band, int32_t *level, int32_t *slot,
+                      int32_t *width, int32_t *height, int64_t *offset);
+/* Coefficients (int32) of one component / one whole picture (Y,C1,C2 consecutive). */
+int64_t vc2b_component_coeff_count(const vc2b_params *p, int comp);
+int64_t vc2b_picture_coeff_count(const vc2b_params *p);
+/* Padded (transform) dimensions and decoded sample count of a picture (Y,C1,C2 planes). */
+int vc2b_padded_dims(const vc2b_params *p, int comp, int32_t *width, int32_t *height);
+int64_t vc2b_picture_sample_count(const vc2b_params *p);
+/* Bytes of scratch one picture needs in vc2b_idwt / vc2b_dwt (intermediate LL bands). */
+int64_t vc2b_transform_scratch_bytes(const vc2b_params *p);
+
+/* ---- decoder ------------------------------------------------------------------------ */
+
+/* HQ slice offsets: the dependent chain hidden in the sequential reader of
+ * hq_slice (decoder/transform_data_syntax.py:212-251; each slice's start is known only after
+ * the three length bytes of the previous one).
+ *   d_data        transform-data bytes of all pictures, back to back; must be followed by at
+ *                 least 16 readable padding bytes
+ *   d_pic_offset  [npictures+1] int64: byte offset of each picture's transform data in d_data;
+ *                 entry i+1 bounds picture i (reads past it are UnexpectedEndOfStream)
+ *   d_slice_offset [npictures*slices] uint32 out: start of each slice relative to its picture
+ *   d_status      [npictures*4] int32 out: {status, first bad slice, bytes consumed, max |coeff|}
+ */
+int vc2b_hq_slice_offsets(const vc2b_params *p, const uint8_t *d_data, const int64_t *d_pic_offset,
+                          int npictures, uint32_t *d_slice_offset, int32_t *d_status, void *stream);
+
+/* transform_data (decoder/transform_data_syntax.py:116): slice unpack (hq_slice :212 / ld_slice
+ * :145, slice_band :286, color_diff_slice_band :315, read_sintb decoder/io.py:307), fused
+ * inverse_quant (pseudocode/quantization.py:18) and, for LD, dc_prediction (:63).
+ *   d_slice_offset from vc2b_hq_slice_offsets (ignored for LD: offsets are closed-form)
+ *   d_coeffs      [npictures * vc2b_picture_coeff_count] int32 out
+ *   d_qindex      [npictures*slices] int32 out (per-slice qindex, for the level-constraint
+ *                 checks the host keeps: transform_data_syntax.py:154,222), may be NULL
+ *   d_status      as above; d_status must have been initialised by vc2b_hq_slice_offsets for HQ;
+ *                 for LD this call initialises it.
+ */
+int vc2b_unpack(const vc2b_params *p, const uint8_t *d_data, const int64_t *d_pic_offset,
+                int npictures, const uint32_t *d_slice_offset, int32_t *d_coeffs,
+                int32_t *d_qindex, int32_t *d_status, void *stream);
+
+/* dc_prediction (decoder/transform_data_syntax.py:63) of the level-0 band of every component,
+ * in place.  vc2b_unpack already applies it for LD; exposed for the function-level API. */
+int vc2b_dc_prediction(const vc2b_params *p, int32_t *d_coeffs, int npictures, int inverse,
+                       void *stream);
+
+/* picture_decode (pseudocode/picture_decoding.py:45): idwt :88 (h_synthesis :134, vh_synthesis
+ * :159, lift1-4 :205-261, filter_bit_shift :198), idwt_pad_removal :282, clip_picture :327,
+ * offset_picture :301.
+ *   d_pictures  [npictures * vc2b_picture_sample_count] uint16 out: planes Y, C1, C2, each
+ *               width x height row-major, values in [0, 2^depth)
+ *   d_scratch   scratch_bytes >= vc2b_transform_scratch_bytes(p); more lets more pictures be
+ *               in flight per launch */
+int vc2b_idwt(const vc2b_params *p, const int32_t *d_coeffs, int npictures, uint16_t *d_pictures,
+              void *d_scratch, int64_t scratch_bytes, void *stream);
+/* idwt (:88) alone for ONE component: no crop, clip or offset; int32 out, padded dimensions. */
+int vc2b_idwt_raw(const vc2b_params *p, int comp, const int32_t *d_coeffs, int32_t *d_out,
+                  void *d_scratch, int64_t scratch_bytes, void *stream);
+
+/* ---- encoder mirror ------------------------------------------------------------- */
+
+/* picture_encode (pseudocode/picture_encoding.py:45): remove_offset_picture :264,
+ * dwt_pad_addition :235, dwt :93 (h_analysis :141, vh_analysis :169).  Layouts as above. */
+int vc2b_dwt(const vc2b_params *p, const uint16_t *d_pictures, int npictures, int32_t *d_coeffs,
+             void *d_scratch, int64_t scratch_bytes, void *stream);
+/* dwt (:93) alone for ONE component from an int32 padded picture (consumed). */
+int vc2b_dwt_raw(const vc2b_params *p, int comp, const int32_t *d_in, int32_t *d_coeffs,
+                 void *d_scratch, int64_t scratch_bytes, void *stream);
+
+/* quantize_to_fit (encoder/pictures.py:295) for every slice of every picture, as driven by
+ * make_transform_data_hq_lossy (:617, align 8*slice_size_scaler, target from picture_bytes) or
+ * make_transform_data_ld_lossy (:724, align 1, target from slice_bytes): the smallest
+ * qindex >= minimum_qindex whose quantised (forward_quant, quantization.py:30) slice fits,
+ * sizes by calculate_coeffs_bits (:217).  For LD the caller applies dc prediction first
+ * (vc2b_dc_prediction with inverse=1).
+ *   picture_bytes  HQ only (LD uses slice_bytes_numerator/denominator)
+ *   d_qindex       [npictures*slices] int32 out
+ *   d_slice_bits   [npictures*slices*3] int32 out: bits of the Y, C1, C2 (LD: Y, C, 0) blocks at
+ *                  the chosen qindex (calculate_coeffs_bits), may be NULL */
+int vc2b_quantize_to_fit(const vc2b_params *p, const int32_t *d_coeffs, int npictures,
+                         int64_t picture_bytes, int minimum_qindex, int32_t *d_qindex,
+                         int32_t *d_slice_bits, void *stream);
+
+/* Slice packing: the serialisation of hq_slice / ld_slice (bitstream/vc2.py:727-839) with
+ * write_sint (bitstream/io.py:575) of the coefficients quantised at d_qindex, producing the
+ * same bytes as make_transform_data_hq_lossy/ld_lossy + autofill_and_serialise_stream.
+ *   d_out        [npictures * out_stride] bytes out (zero prefix bytes for HQ)
+ *   out_stride   >= vc2b_packed_bytes(p, picture_bytes), a multiple of 4; d_out 4-byte aligned */
+int64_t vc2b_packed_bytes(const vc2b_params *p, int64_t picture_bytes);
+int vc2b_pack_slices(const vc2b_params *p, const int32_t *d_coeffs, int npictures,
+                     int64_t picture_bytes, const int32_t *d_qindex, const int32_t *d_slice_bits,
+                     uint8_t *d_out, int64_t out_stride, void *stream);
+
+/* ---- element-wise pseudocode functions ---------------------------------------------- */
+/* inverse_quant / forward_quant (pseudocode/quantization.py:18,30) with per-element index. */
+int vc2b_inverse_quant(const int32_t *d_in, const int32_t *d_qi, int32_t *d_out, int64_t n,
+                       void *stream);
+int vc2b_forward_quant(const int32_t *d_in, const int32_t *d_qi, int32_t *d_out, int64_t n,
+                       void *stream);
+/* clip_component + offset_component (pseudocode/picture_decoding.py:301-349) on int32 data:
+ * mode bit0 = clip, bit1 = add offset, bit2 = subtract offset (remove_offset, :264). */
+int vc2b_clip_offset(int32_t *d_data, int64_t n, int depth, int mode, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VC2_B200_H */

@@ -1,0 +1,117 @@
+"""
+ctypes binding of libvc2b200.so (include/vc2_b200.h).  There is NO fallback: if the CUDA
+library has not been built, importing this module's `lib()` raises.
+"""
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_lib", "libvc2b200.so")
+
+MAX_LEVELS = 16
+MAX_BANDS = 32
+
+E_BAD_PARAMS = -1
+E_UNSUPPORTED = -2
+E_SCRATCH_TOO_SMALL = -3
+
+ST_OK = 0
+ST_UNEXPECTED_END_OF_STREAM = 1
+ST_INVALID_SLICE_Y_LENGTH = 2
+ST_INT32_ENVELOPE = 4
+
+
+class Params(C.Structure):
+    """struct vc2b_params (include/vc2_b200.h)."""
+
+    _fields_ = [
+        ("luma_width", C.c_int32),
+        ("luma_height", C.c_int32),
+        ("color_diff_width", C.c_int32),
+        ("color_diff_height", C.c_int32),
+        ("luma_depth", C.c_int32),
+        ("color_diff_depth", C.c_int32),
+        ("wavelet_index", C.c_int32),
+        ("wavelet_index_ho", C.c_int32),
+        ("dwt_depth", C.c_int32),
+        ("dwt_depth_ho", C.c_int32),
+        ("slices_x", C.c_int32),
+        ("slices_y", C.c_int32),
+        ("is_ld", C.c_int32),
+        ("slice_prefix_bytes", C.c_int32),
+        ("slice_size_scaler", C.c_int32),
+        ("slice_bytes_numerator", C.c_int64),
+        ("slice_bytes_denominator", C.c_int64),
+        ("quant_matrix", (C.c_int32 * 4) * MAX_LEVELS),
+    ]
+
+
+class LibraryMissing(ImportError):
+    pass
+
+
+class Vc2bError(RuntimeError):
+    def __init__(self, fn, code):
+        self.code = code
+        names = {-1: "bad parameters", -2: "unsupported parameters", -3: "scratch buffer too small"}
+        what = names.get(code, "CUDA error %d" % code)
+        RuntimeError.__init__(self, "%s failed: %s" % (fn, what))
+
+
+_lib = None
+
+_PP = C.POINTER(Params)
+_vp = C.c_void_p
+_i = C.c_int
+_i64 = C.c_int64
+
+# name -> (restype, argtypes); every symbol include/vc2_b200.h declares
+SIGNATURES = {
+    "vc2b_version": (C.c_char_p, []),
+    "vc2b_check_params": (_i, [_PP]),
+    "vc2b_num_subbands": (_i, [_PP]),
+    "vc2b_subband_info": (_i, [_PP, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "vc2b_component_coeff_count": (_i64, [_PP, _i]),
+    "vc2b_picture_coeff_count": (_i64, [_PP]),
+    "vc2b_padded_dims": (_i, [_PP, _i, _vp, _vp]),
+    "vc2b_picture_sample_count": (_i64, [_PP]),
+    "vc2b_transform_scratch_bytes": (_i64, [_PP]),
+    "vc2b_hq_slice_offsets": (_i, [_PP, _vp, _vp, _i, _vp, _vp, _vp]),
+    "vc2b_unpack": (_i, [_PP, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "vc2b_dc_prediction": (_i, [_PP, _vp, _i, _i, _vp]),
+    "vc2b_idwt": (_i, [_PP, _vp, _i, _vp, _vp, _i64, _vp]),
+    "vc2b_idwt_raw": (_i, [_PP, _i, _vp, _vp, _vp, _i64, _vp]),
+    "vc2b_dwt": (_i, [_PP, _vp, _i, _vp, _vp, _i64, _vp]),
+    "vc2b_dwt_raw": (_i, [_PP, _i, _vp, _vp, _vp, _i64, _vp]),
+    "vc2b_quantize_to_fit": (_i, [_PP, _vp, _i, _i64, _i, _vp, _vp, _vp]),
+    "vc2b_packed_bytes": (_i64, [_PP, _i64]),
+    "vc2b_pack_slices": (_i, [_PP, _vp, _i, _i64, _vp, _vp, _vp, _i64, _vp]),
+    "vc2b_inverse_quant": (_i, [_vp, _vp, _vp, _i64, _vp]),
+    "vc2b_forward_quant": (_i, [_vp, _vp, _vp, _i64, _vp]),
+    "vc2b_clip_offset": (_i, [_vp, _i64, _i, _i, _vp]),
+}
+
+
+def lib():
+    """Loads libvc2b200.so; raises LibraryMissing (no CPU fallback exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LibraryMissing(
+            "%s not found: build it with `python -m vc2_conformance_b200._build` "
+            "(there is no CPU fallback)" % LIB_PATH
+        )
+    L = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        f = getattr(L, name)
+        f.restype = res
+        f.argtypes = args
+    _lib = L
+    return L
+
+
+def check(fn, code):
+    if code != 0:
+        raise Vc2bError(fn, code)

@@ -1,0 +1,170 @@
+// params.cu -- host-side geometry and introspection entry points of libvc2b200.
+//
+// Restates pseudocode/slice_sizes.py:53-92 (subband_width / subband_height) and
+// the subband ordering of decoder/transform_data_syntax.py:176-189,230-243.
+#include "common.cuh"
+
+namespace vc2b {
+
+static int32_t subband_width(const vc2b_params *p, int level, int comp)
+{
+    int32_t w = comp == 0 ? p->luma_width : p->color_diff_width;
+    int32_t scale_w = 1 << (p->dwt_depth_ho + p->dwt_depth);
+    int32_t pw = scale_w * ((w + scale_w - 1) / scale_w);
+    if (level == 0) return pw / scale_w;
+    return pw / (1 << (p->dwt_depth_ho + p->dwt_depth - level + 1));
+}
+
+static int32_t subband_height(const vc2b_params *p, int level, int comp)
+{
+    int32_t h = comp == 0 ? p->luma_height : p->color_diff_height;
+    int32_t scale_h = 1 << p->dwt_depth;
+    int32_t ph = scale_h * ((h + scale_h - 1) / scale_h);
+    if (level == 0 || level <= p->dwt_depth_ho) return ph / scale_h;
+    return ph / (1 << (p->dwt_depth_ho + p->dwt_depth - level + 1));
+}
+
+int make_dev_params(const vc2b_params *p, DevParams *d)
+{
+    if (!p || !d) return VC2B_E_BAD_PARAMS;
+    if (p->luma_width < 1 || p->luma_height < 1 || p->color_diff_width < 1 ||
+        p->color_diff_height < 1)
+        return VC2B_E_BAD_PARAMS;
+    if (p->luma_depth < 1 || p->luma_depth > 16 || p->color_diff_depth < 1 ||
+        p->color_diff_depth > 16)
+        return VC2B_E_UNSUPPORTED;
+    if (p->wavelet_index < 0 || p->wavelet_index > 6 || p->wavelet_index_ho < 0 ||
+        p->wavelet_index_ho > 6)
+        return VC2B_E_BAD_PARAMS;
+    if (p->dwt_depth < 0 || p->dwt_depth_ho < 0 || p->dwt_depth + p->dwt_depth_ho + 1 > VC2B_MAX_LEVELS)
+        return VC2B_E_BAD_PARAMS;
+    int nb = 1 + p->dwt_depth_ho + 3 * p->dwt_depth;
+    if (nb > kMaxBands) return VC2B_E_UNSUPPORTED;
+    if (p->slices_x < 1 || p->slices_y < 1) return VC2B_E_BAD_PARAMS;
+    if (p->is_ld) {
+        if (p->slice_bytes_denominator < 1 || p->slice_bytes_numerator < 0) return VC2B_E_BAD_PARAMS;
+    } else {
+        if (p->slice_prefix_bytes < 0 || p->slice_size_scaler < 1) return VC2B_E_BAD_PARAMS;
+    }
+
+    memset(d, 0, sizeof(*d));
+    d->wavelet_index = p->wavelet_index;
+    d->wavelet_index_ho = p->wavelet_index_ho;
+    d->dwt_depth = p->dwt_depth;
+    d->dwt_depth_ho = p->dwt_depth_ho;
+    d->slices_x = p->slices_x;
+    d->slices_y = p->slices_y;
+    d->is_ld = p->is_ld ? 1 : 0;
+    d->slice_prefix_bytes = p->slice_prefix_bytes;
+    d->slice_size_scaler = p->slice_size_scaler;
+    d->sb_num = p->slice_bytes_numerator;
+    d->sb_den = p->slice_bytes_denominator;
+    d->nb = nb;
+    int top = p->dwt_depth + p->dwt_depth_ho;
+    int64_t coeff_total = 0, sample_total = 0;
+    for (int c = 0; c < 3; c++) {
+        d->width[c] = c == 0 ? p->luma_width : p->color_diff_width;
+        d->height[c] = c == 0 ? p->luma_height : p->color_diff_height;
+        d->depth[c] = c == 0 ? p->luma_depth : p->color_diff_depth;
+        int b = 0;
+        int64_t off = 0;
+        for (int lv = 0; lv <= top; lv++) {
+            int no = (lv == 0) ? 1 : (lv <= p->dwt_depth_ho ? 1 : 3);
+            for (int o = 0; o < no; o++, b++) {
+                Band &B = d->band[c][b];
+                B.w = subband_width(p, lv, c);
+                B.h = subband_height(p, lv, c);
+                B.level = lv;
+                B.slot = (lv == 0) ? 0 : o + 1;
+                B.off = (int32_t)off;
+                B.qm = p->quant_matrix[lv][B.slot];
+                off += (int64_t)B.w * B.h;
+            }
+        }
+        d->pw[c] = (top == 0) ? d->band[c][0].w : 2 * d->band[c][nb - 1].w;
+        d->ph[c] = (p->dwt_depth == 0) ? d->band[c][0].h : 2 * d->band[c][nb - 1].h;
+        if (off != (int64_t)d->pw[c] * d->ph[c]) return VC2B_E_BAD_PARAMS;
+        d->comp_off[c] = (int32_t)coeff_total;
+        d->comp_count[c] = (int32_t)off;
+        coeff_total += off;
+        d->pic_off[c] = (int32_t)sample_total;
+        sample_total += (int64_t)d->width[c] * d->height[c];
+        if (coeff_total > 0x7fffffffLL || sample_total > 0x7fffffffLL) return VC2B_E_UNSUPPORTED;
+    }
+    d->pic_coeffs = (int32_t)coeff_total;
+    d->pic_samples = (int32_t)sample_total;
+    return 0;
+}
+
+}  // namespace vc2b
+
+using namespace vc2b;
+
+extern "C" {
+
+const char *vc2b_version(void) { return "vc2b200 0.1 (sm_100a)"; }
+
+int vc2b_check_params(const vc2b_params *p)
+{
+    DevParams d;
+    return make_dev_params(p, &d);
+}
+
+int vc2b_num_subbands(const vc2b_params *p)
+{
+    DevParams d;
+    int st = make_dev_params(p, &d);
+    return st ? st : d.nb;
+}
+
+int vc2b_subband_info(const vc2b_params *p, int comp, int band, int32_t *level, int32_t *slot,
+                      int32_t *width, int32_t *height, int64_t *offset)
+{
+    DevParams d;
+    int st = make_dev_params(p, &d);
+    if (st) return st;
+    if (comp < 0 || comp > 2 || band < 0 || band >= d.nb) return VC2B_E_BAD_PARAMS;
+    const Band &B = d.band[comp][band];
+    if (level) *level = B.level;
+    if (slot) *slot = B.slot;
+    if (width) *width = B.w;
+    if (height) *height = B.h;
+    if (offset) *offset = B.off;
+    return 0;
+}
+
+int64_t vc2b_component_coeff_count(const vc2b_params *p, int comp)
+{
+    DevParams d;
+    int st = make_dev_params(p, &d);
+    if (st) return st;
+    if (comp < 0 || comp > 2) return VC2B_E_BAD_PARAMS;
+    return d.comp_count[comp];
+}
+
+int64_t vc2b_picture_coeff_count(const vc2b_params *p)
+{
+    DevParams d;
+    int st = make_dev_params(p, &d);
+    return st ? st : d.pic_coeffs;
+}
+
+int vc2b_padded_dims(const vc2b_params *p, int comp, int32_t *width, int32_t *height)
+{
+    DevParams d;
+    int st = make_dev_params(p, &d);
+    if (st) return st;
+    if (comp < 0 || comp > 2) return VC2B_E_BAD_PARAMS;
+    if (width) *width = d.pw[comp];
+    if (height) *height = d.ph[comp];
+    return 0;
+}
+
+int64_t vc2b_picture_sample_count(const vc2b_params *p)
+{
+    DevParams d;
+    int st = make_dev_params(p, &d);
+    return st ? st : d.pic_samples;
+}
+
+}  // extern "C"

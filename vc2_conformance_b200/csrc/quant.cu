@@ -1,0 +1,503 @@
+// quant.cu -- quantiser kernels: element-wise inverse/forward quantisation, the per-slice
+// quantisation-index search of the encoder, and slice bit-packing.
+//
+// Replaces inverse_quant / forward_quant / quant_factor / quant_offset
+// (pseudocode/quantization.py:18-62), clip/offset components
+// (pseudocode/picture_decoding.py:301-349), quantize_coeffs / calculate_coeffs_bits /
+// quantize_to_fit (encoder/pictures.py:217-347) as driven by make_transform_data_hq_lossy
+// (:617) and make_transform_data_ld_lossy (:724), and the serialisation of hq_slice / ld_slice
+// (bitstream/vc2.py:727-839) with write_sint (bitstream/io.py:557-583).
+#include "common.cuh"
+
+namespace vc2b {
+
+constexpr int kQWarps = 4;
+
+// ---------------------------------------------------------------------------
+// element-wise
+// ---------------------------------------------------------------------------
+
+__device__ __forceinline__ int32_t inverse_quant_dev(int32_t q, int qi, bool *overflow)
+{
+    if (q == 0) return 0;
+    const uint32_t m = q < 0 ? (uint32_t)(-(long long)q) : (uint32_t)q;
+    const unsigned long long t = ((unsigned long long)m * quant_factor_u64(qi) + quant_offset_u64(qi) + 2) >> 2;
+    if (t > 0x7fffffffull) *overflow = true;
+    return q < 0 ? -(int32_t)t : (int32_t)t;
+}
+
+// forward_quant (quantization.py:30): sign(c) * ((4*|c|) // quant_factor)
+__device__ __forceinline__ uint32_t forward_quant_mag(uint32_t m, unsigned long long qf)
+{
+    const unsigned long long num = 4ull * m;
+    if (((num | qf) >> 32) == 0) return (uint32_t)num / (uint32_t)qf;
+    return (uint32_t)(num / qf);
+}
+
+__global__ void inverse_quant_kernel(const int32_t *__restrict__ in, const int32_t *__restrict__ qi,
+                                     int32_t *__restrict__ out, long long n)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        bool ov = false;
+        out[i] = inverse_quant_dev(in[i], max(qi[i], 0), &ov);
+    }
+}
+
+__global__ void forward_quant_kernel(const int32_t *__restrict__ in, const int32_t *__restrict__ qi,
+                                     int32_t *__restrict__ out, long long n)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int32_t c = in[i];
+        const uint32_t m = c < 0 ? (uint32_t)(-(long long)c) : (uint32_t)c;
+        const uint32_t r = forward_quant_mag(m, quant_factor_u64(max(qi[i], 0)));
+        out[i] = c < 0 ? -(int32_t)r : (int32_t)r;
+    }
+}
+
+__global__ void clip_offset_kernel(int32_t *__restrict__ data, long long n, int depth, int mode)
+{
+    const int half = 1 << (depth - 1);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        int v = data[i];
+        if (mode & 1) v = min(max(v, -half), half - 1);
+        if (mode & 2) v += half;
+        if (mode & 4) v -= half;
+        data[i] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// per-slice tables shared by the qindex search and the packer
+// ---------------------------------------------------------------------------
+
+struct SliceBands {
+    int32_t cum[kMaxBands + 1];
+    int32_t w[kMaxBands];
+    int32_t stride[kMaxBands];
+    int32_t base[kMaxBands];
+    int32_t qm[kMaxBands];
+};
+
+__device__ __forceinline__ int build_slice_bands(const DevParams &P, int comp, int sx, int sy, SliceBands &T,
+                                                 int lane)
+{
+    const int nb = P.nb;
+    int cnt = 0;
+    if (lane < nb) {
+        const Band &B = P.band[comp][lane];
+        int x1 = (int)(((long long)B.w * sx) / P.slices_x);
+        int x2 = (int)(((long long)B.w * (sx + 1)) / P.slices_x);
+        int y1 = (int)(((long long)B.h * sy) / P.slices_y);
+        int y2 = (int)(((long long)B.h * (sy + 1)) / P.slices_y);
+        T.w[lane] = max(x2 - x1, 1);
+        T.stride[lane] = B.w;
+        T.base[lane] = B.off + y1 * B.w + x1;
+        T.qm[lane] = B.qm;
+        cnt = (x2 - x1) * (y2 - y1);
+    }
+    int pre = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int o = __shfl_up_sync(0xffffffffu, pre, d);
+        if (lane >= d) pre += o;
+    }
+    if (lane < nb) T.cum[lane + 1] = pre;
+    if (lane == 0) T.cum[0] = 0;
+    __syncwarp();
+    return __shfl_sync(0xffffffffu, pre, 31);
+}
+
+// coefficient j (bitstream order, encoder/pictures.py:418-451) of the slice component
+__device__ __forceinline__ int32_t slice_coeff(const SliceBands &T, int nb, const int32_t *__restrict__ comp,
+                                               int j, int *band)
+{
+    int b = 0;
+    while (b < nb - 1 && j >= T.cum[b + 1]) b++;
+    const int local = j - T.cum[b];
+    const int y = local / T.w[b];
+    const int x = local - y * T.w[b];
+    *band = b;
+    return comp[T.base[b] + y * T.stride[b] + x];
+}
+
+// signed_exp_golomb_length (bitstream/exp_golomb.py:28)
+__device__ __forceinline__ int sint_length(uint32_t mag)
+{
+    if (mag == 0) return 1;
+    const int k = 31 - __clz(mag + 1u);  // mag <= 2^31: no wrap
+    return 2 * k + 2;
+}
+
+// calculate_coeffs_bits (encoder/pictures.py:217) of one slice component quantised at qindex
+// (quantize_coeffs :251).  INTERLEAVED: C1/C2 interleaved per coefficient (:712).
+template <bool INTERLEAVED>
+__device__ int slice_bits(const SliceBands &T, int nb, const int32_t *__restrict__ c1,
+                          const int32_t *__restrict__ c2, int ncoef, int qindex, int lane)
+{
+    int sum = 0, last = -1;
+    for (int idx = lane; idx < ncoef; idx += 32) {
+        const int j = INTERLEAVED ? (idx >> 1) : idx;
+        int b;
+        const int32_t c = slice_coeff(T, nb, (INTERLEAVED && (idx & 1)) ? c2 : c1, j, &b);
+        const uint32_t m = c < 0 ? (uint32_t)(-(long long)c) : (uint32_t)c;
+        const uint32_t q = forward_quant_mag(m, quant_factor_u64(max(qindex - T.qm[b], 0)));
+        sum += sint_length(q);
+        if (q != 0) last = idx;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, d);
+        last = max(last, __shfl_xor_sync(0xffffffffu, last, d));
+    }
+    return sum - (ncoef - 1 - last);  // trailing zeros are free
+}
+
+struct FitArgs {
+    long long total_coeff_bytes;  // HQ: picture_bytes - 4*slices
+    int minimum_qindex;
+    int max_qm;
+};
+
+__device__ __forceinline__ long long hq_total_length(const DevParams &P, const FitArgs &F, long long n)
+{
+    // slice_bytes (slice_sizes.py:95) re-purposed by make_transform_data_hq_lossy (:672-690)
+    const long long den = (long long)P.slices_x * P.slices_y * P.slice_size_scaler;
+    return ((n + 1) * F.total_coeff_bytes) / den - (n * F.total_coeff_bytes) / den;
+}
+
+__global__ void __launch_bounds__(kQWarps * 32)
+quantize_fit_kernel(DevParams P, FitArgs F, const int32_t *__restrict__ coeffs, int npictures,
+                    int32_t *__restrict__ qindex_out, int32_t *__restrict__ bits_out)
+{
+    __shared__ SliceBands tabs[kQWarps][2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nslices = P.slices_x * P.slices_y;
+    const long long gw = (long long)blockIdx.x * kQWarps + warp;
+    if (gw >= (long long)npictures * nslices) return;
+    const int pic = (int)(gw / nslices);
+    const int n = (int)(gw - (long long)pic * nslices);
+    const int sy = n / P.slices_x, sx = n - sy * P.slices_x;
+    const int32_t *pc = coeffs + (size_t)pic * P.pic_coeffs;
+    SliceBands &TY = tabs[warp][0];
+    SliceBands &TC = tabs[warp][1];
+    const int ny = build_slice_bands(P, 0, sx, sy, TY, lane);
+    const int nc = build_slice_bands(P, 1, sx, sy, TC, lane);
+
+    long long target, align;
+    if (P.is_ld) {
+        const long long sb = ld_slice_offset(P, n + 1) - ld_slice_offset(P, n);
+        target = 8 * sb - 7;
+        target -= ilog2_ceil(target);
+        align = 1;
+    } else {
+        align = 8LL * P.slice_size_scaler;
+        target = align * hq_total_length(P, F, n);
+    }
+
+    int by = 0, bc1 = 0, bc2 = 0;
+    auto fits = [&](int q) -> bool {
+        by = slice_bits<false>(TY, P.nb, pc + P.comp_off[0], nullptr, ny, q, lane);
+        long long total;
+        if (P.is_ld) {
+            bc1 = slice_bits<true>(TC, P.nb, pc + P.comp_off[1], pc + P.comp_off[2], 2 * nc, q, lane);
+            bc2 = 0;
+            total = (long long)by + bc1;
+        } else {
+            bc1 = slice_bits<false>(TC, P.nb, pc + P.comp_off[1], nullptr, nc, q, lane);
+            bc2 = slice_bits<false>(TC, P.nb, pc + P.comp_off[2], nullptr, nc, q, lane);
+            total = ((by + align - 1) / align + (bc1 + align - 1) / align + (bc2 + align - 1) / align) * align;
+        }
+        return total <= target;
+    };
+
+    // The total is non-increasing in qindex (|forward_quant| is non-increasing in the quantiser),
+    // so the reference's linear search (quantize_to_fit :329) equals this bisection.
+    int lo = F.minimum_qindex;
+    int hi = max(lo, 128 + F.max_qm + 4);  // everything quantises to zero here (int32 envelope)
+    if (target < 0) {
+        lo = hi;  // cannot fit: reported as the saturated index (the reference would not terminate)
+    } else {
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (fits(mid)) hi = mid; else lo = mid + 1;
+        }
+    }
+    fits(lo);
+    if (lane == 0) {
+        qindex_out[gw] = lo;
+        if (bits_out) {
+            bits_out[3 * gw + 0] = by;
+            bits_out[3 * gw + 1] = bc1;
+            bits_out[3 * gw + 2] = bc2;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// slice packing
+// ---------------------------------------------------------------------------
+
+// OR `len` (<= 64) bits of `code` (right-aligned) into the big-endian bit string `out32` at
+// absolute bit position `pos`; bits at or beyond `end` are dropped (1-bits past the end of a
+// bounded block are not written: bitstream/io.py:457-470).
+__device__ __forceinline__ void put_bits(uint32_t *__restrict__ out32, long long pos, unsigned long long code,
+                                         int len, long long end)
+{
+    if (pos + len > end) {
+        const long long drop = pos + len - end;
+        if (drop >= len) return;
+        code >>= drop;
+        len -= (int)drop;
+    }
+    if (len <= 0) return;
+    const long long w0 = pos >> 5;
+    const int o = (int)(pos & 31);
+    // 96-bit window [w0, w0+3): place the code so that its MSB sits at bit offset o
+    const int sh = 96 - o - len;  // >= 0
+    uint32_t p0 = 0, p1 = 0, p2 = 0;
+    // value = code << sh as three 32-bit words (p0 most significant)
+    if (sh >= 64) {
+        p0 = (uint32_t)(code << (sh - 64));
+    } else if (sh >= 32) {
+        const unsigned long long t = code << (sh - 32);  // len + sh - 32 <= 64 bits
+        p1 = (uint32_t)t;
+        p0 = (uint32_t)(t >> 32);
+    } else {
+        p2 = (uint32_t)(code << sh);
+        p1 = (uint32_t)(sh == 0 ? (code >> 32) : (code >> (32 - sh)));
+        p0 = (uint32_t)(sh == 0 ? 0 : (code >> (64 - sh)));
+    }
+    if (p0) atomicOr(&out32[w0], __byte_perm(p0, 0, 0x0123));
+    if (p1) atomicOr(&out32[w0 + 1], __byte_perm(p1, 0, 0x0123));
+    if (p2) atomicOr(&out32[w0 + 2], __byte_perm(p2, 0, 0x0123));
+}
+
+// write_sint (bitstream/io.py:575): code bits right-aligned, and its length
+__device__ __forceinline__ unsigned long long sint_code(int32_t v, int *len)
+{
+    if (v == 0) { *len = 1; return 1ull; }
+    const uint32_t mag = v < 0 ? (uint32_t)(-(long long)v) : (uint32_t)v;
+    const unsigned long long m = (unsigned long long)mag + 1;
+    const int k = 63 - __clzll((long long)m);
+    unsigned long long d = m - (1ull << k);  // k data bits
+    // spread: bit i of d -> bit 2i
+    d = (d | (d << 16)) & 0x0000ffff0000ffffull;
+    d = (d | (d << 8)) & 0x00ff00ff00ff00ffull;
+    d = (d | (d << 4)) & 0x0f0f0f0f0f0f0f0full;
+    d = (d | (d << 2)) & 0x3333333333333333ull;
+    d = (d | (d << 1)) & 0x5555555555555555ull;
+    *len = 2 * k + 2;
+    return (((d << 1) | 1ull) << 1) | (v < 0 ? 1ull : 0ull);
+}
+
+// Packs one bounded block: values in bitstream order at absolute bit `start`, block end `end`.
+template <bool INTERLEAVED>
+__device__ void pack_block(const SliceBands &T, int nb, const int32_t *__restrict__ c1,
+                           const int32_t *__restrict__ c2, int ncoef, int qindex, uint32_t *__restrict__ out32,
+                           long long start, long long end, int lane)
+{
+    long long pos = start;
+    for (int i0 = 0; i0 < ncoef && pos < end; i0 += 32) {
+        const int idx = i0 + lane;
+        int len = 0;
+        unsigned long long code = 0;
+        if (idx < ncoef) {
+            const int j = INTERLEAVED ? (idx >> 1) : idx;
+            int b;
+            const int32_t c = slice_coeff(T, nb, (INTERLEAVED && (idx & 1)) ? c2 : c1, j, &b);
+            const uint32_t m = c < 0 ? (uint32_t)(-(long long)c) : (uint32_t)c;
+            const uint32_t q = forward_quant_mag(m, quant_factor_u64(max(qindex - T.qm[b], 0)));
+            code = sint_code(c < 0 ? -(int32_t)q : (int32_t)q, &len);
+        }
+        int pre = len;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int o = __shfl_up_sync(0xffffffffu, pre, d);
+            if (lane >= d) pre += o;
+        }
+        if (len) put_bits(out32, pos + pre - len, code, len, end);
+        pos += __shfl_sync(0xffffffffu, pre, 31);
+    }
+}
+
+__global__ void __launch_bounds__(kQWarps * 32)
+pack_slices_kernel(DevParams P, FitArgs F, const int32_t *__restrict__ coeffs, int npictures,
+                   const int32_t *__restrict__ qindex_in, const int32_t *__restrict__ bits_in,
+                   uint8_t *__restrict__ out, long long out_stride)
+{
+    __shared__ SliceBands tabs[kQWarps][2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nslices = P.slices_x * P.slices_y;
+    const long long gw = (long long)blockIdx.x * kQWarps + warp;
+    if (gw >= (long long)npictures * nslices) return;
+    const int pic = (int)(gw / nslices);
+    const int n = (int)(gw - (long long)pic * nslices);
+    const int sy = n / P.slices_x, sx = n - sy * P.slices_x;
+    const int32_t *pc = coeffs + (size_t)pic * P.pic_coeffs;
+    SliceBands &TY = tabs[warp][0];
+    SliceBands &TC = tabs[warp][1];
+    const int ny = build_slice_bands(P, 0, sx, sy, TY, lane);
+    const int nc = build_slice_bands(P, 1, sx, sy, TC, lane);
+    const int qindex = qindex_in[gw];
+    uint32_t *out32 = reinterpret_cast<uint32_t *>(out);  // out is 4-byte aligned; positions absolute
+    const long long pic_bit0 = 8 * (long long)pic * out_stride;
+
+    if (P.is_ld) {
+        // ld_slice (bitstream/vc2.py:727): 7-bit qindex, slice_y_length, luma block, chroma block
+        const long long s0 = ld_slice_offset(P, n), s1 = ld_slice_offset(P, n + 1);
+        const long long sb = s1 - s0;
+        const int length_bits = ilog2_ceil(8 * sb - 7);
+        const long long y_len = bits_in[3 * gw + 0];
+        long long pos = pic_bit0 + 8 * s0;
+        const long long end = pic_bit0 + 8 * s1;
+        if (lane == 0) {
+            put_bits(out32, pos, (unsigned long long)qindex, 7, end);
+            put_bits(out32, pos + 7, (unsigned long long)y_len, length_bits, end);
+        }
+        pos += 7 + length_bits;
+        pack_block<false>(TY, P.nb, pc + P.comp_off[0], nullptr, ny, qindex, out32, pos, pos + y_len, lane);
+        pos += y_len;
+        pack_block<true>(TC, P.nb, pc + P.comp_off[1], pc + P.comp_off[2], 2 * nc, qindex, out32, pos, end, lane);
+    } else {
+        // hq_slice (bitstream/vc2.py:798): prefix bytes (zero), qindex, then per component a
+        // length byte and a bounded block of 8*scaler*length bits (make_hq_slice :456)
+        const long long scaler = P.slice_size_scaler;
+        const long long den = (long long)nslices * scaler;
+        const long long off = (long long)n * (P.slice_prefix_bytes + 4) + scaler * ((n * F.total_coeff_bytes) / den);
+        const long long total_length = hq_total_length(P, F, n);
+        const long long align = 8 * scaler;
+        const long long ly = (bits_in[3 * gw + 0] + align - 1) / align;
+        const long long l1 = (bits_in[3 * gw + 1] + align - 1) / align;
+        const long long l2 = total_length - ly - l1;
+        long long pos = pic_bit0 + 8 * (off + P.slice_prefix_bytes);
+        const long long big = 0x7fffffffffffffffLL;
+        if (lane == 0) {
+            put_bits(out32, pos, (unsigned long long)qindex, 8, big);
+            put_bits(out32, pos + 8, (unsigned long long)ly, 8, big);
+        }
+        pos += 16;
+        pack_block<false>(TY, P.nb, pc + P.comp_off[0], nullptr, ny, qindex, out32, pos, pos + align * ly, lane);
+        pos += align * ly;
+        if (lane == 0) put_bits(out32, pos, (unsigned long long)l1, 8, big);
+        pos += 8;
+        pack_block<false>(TC, P.nb, pc + P.comp_off[1], nullptr, nc, qindex, out32, pos, pos + align * l1, lane);
+        pos += align * l1;
+        if (lane == 0) put_bits(out32, pos, (unsigned long long)l2, 8, big);
+        pos += 8;
+        pack_block<false>(TC, P.nb, pc + P.comp_off[2], nullptr, nc, qindex, out32, pos, pos + align * l2, lane);
+    }
+}
+
+static int max_qm(const DevParams &P)
+{
+    int m = 0;
+    for (int b = 0; b < P.nb; b++) m = max(m, P.band[0][b].qm);
+    return m;
+}
+
+}  // namespace vc2b
+
+using namespace vc2b;
+
+static inline unsigned grid_for(long long n, int threads)
+{
+    long long b = (n + threads - 1) / threads;
+    const long long cap = 148LL * 16;
+    return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+extern "C" {
+
+int vc2b_inverse_quant(const int32_t *d_in, const int32_t *d_qi, int32_t *d_out, int64_t n, void *stream)
+{
+    if (n <= 0) return 0;
+    inverse_quant_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(d_in, d_qi, d_out, n);
+    VC2B_CHECK_LAUNCH();
+    return 0;
+}
+
+int vc2b_forward_quant(const int32_t *d_in, const int32_t *d_qi, int32_t *d_out, int64_t n, void *stream)
+{
+    if (n <= 0) return 0;
+    forward_quant_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(d_in, d_qi, d_out, n);
+    VC2B_CHECK_LAUNCH();
+    return 0;
+}
+
+int vc2b_clip_offset(int32_t *d_data, int64_t n, int depth, int mode, void *stream)
+{
+    if (n <= 0) return 0;
+    if (depth < 1 || depth > 30) return VC2B_E_BAD_PARAMS;
+    clip_offset_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(d_data, n, depth, mode);
+    VC2B_CHECK_LAUNCH();
+    return 0;
+}
+
+int vc2b_quantize_to_fit(const vc2b_params *p, const int32_t *d_coeffs, int npictures, int64_t picture_bytes,
+                         int minimum_qindex, int32_t *d_qindex, int32_t *d_slice_bits, void *stream)
+{
+    DevParams P;
+    int st = make_dev_params(p, &P);
+    if (st) return st;
+    if (npictures <= 0) return 0;
+    FitArgs F;
+    const long long nslices = (long long)P.slices_x * P.slices_y;
+    F.total_coeff_bytes = picture_bytes - 4 * nslices;
+    if (!P.is_ld && F.total_coeff_bytes < 0) return VC2B_E_BAD_PARAMS;  // InsufficientHQPictureBytesError
+    F.minimum_qindex = minimum_qindex < 0 ? 0 : minimum_qindex;
+    F.max_qm = max_qm(P);
+    const long long warps = npictures * nslices;
+    quantize_fit_kernel<<<(unsigned)((warps + kQWarps - 1) / kQWarps), kQWarps * 32, 0, (cudaStream_t)stream>>>(
+        P, F, d_coeffs, npictures, d_qindex, d_slice_bits);
+    VC2B_CHECK_LAUNCH();
+    return 0;
+}
+
+int64_t vc2b_packed_bytes(const vc2b_params *p, int64_t picture_bytes)
+{
+    DevParams P;
+    int st = make_dev_params(p, &P);
+    if (st) return st;
+    const long long nslices = (long long)P.slices_x * P.slices_y;
+    long long n;
+    if (P.is_ld) {
+        n = ld_slice_offset(P, nslices);
+    } else {
+        const long long tcb = picture_bytes - 4 * nslices;
+        if (tcb < 0) return VC2B_E_BAD_PARAMS;
+        const long long den = nslices * P.slice_size_scaler;
+        n = nslices * (P.slice_prefix_bytes + 4) + P.slice_size_scaler * ((nslices * tcb) / den);
+    }
+    return n;
+}
+
+int vc2b_pack_slices(const vc2b_params *p, const int32_t *d_coeffs, int npictures, int64_t picture_bytes,
+                     const int32_t *d_qindex, const int32_t *d_slice_bits, uint8_t *d_out, int64_t out_stride,
+                     void *stream)
+{
+    DevParams P;
+    int st = make_dev_params(p, &P);
+    if (st) return st;
+    if (npictures <= 0) return 0;
+    const int64_t need = vc2b_packed_bytes(p, picture_bytes);
+    if (need < 0) return (int)need;
+    if (out_stride < need || (out_stride & 3)) return VC2B_E_BAD_PARAMS;
+    FitArgs F;
+    const long long nslices = (long long)P.slices_x * P.slices_y;
+    F.total_coeff_bytes = picture_bytes - 4 * nslices;
+    F.minimum_qindex = 0;
+    F.max_qm = max_qm(P);
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(d_out, 0, (size_t)out_stride * npictures, s);
+    if (e != cudaSuccess) return (int)e;
+    const long long warps = npictures * nslices;
+    pack_slices_kernel<<<(unsigned)((warps + kQWarps - 1) / kQWarps), kQWarps * 32, 0, s>>>(
+        P, F, d_coeffs, npictures, d_qindex, d_slice_bits, d_out, out_stride);
+    VC2B_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,98 @@
+"""
+numpy-in / numpy-out wrappers of single C-ABI calls (host -> device -> kernel -> host).
+Used by the reference-named functions in ``pseudocode.py`` and by the parity tests; the
+throughput path (``device.BatchCodec``) keeps data resident instead.
+"""
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .device import _ptr, _torch
+from .params import Geometry
+
+
+def _dev(a, dtype):
+    torch = _torch()
+    a = np.ascontiguousarray(a, dtype)
+    if dtype == np.uint16:
+        return torch.from_numpy(a.view(np.int16)).cuda().view(torch.uint16)
+    return torch.from_numpy(a).cuda()
+
+
+def _stream():
+    torch = _torch()
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def idwt_component(p, comp, coeffs):
+    """idwt (pseudocode/picture_decoding.py:88) of one component: flat int32 coefficients in
+    subband order -> int32 array [padded_h, padded_w]."""
+    torch = _torch()
+    g = Geometry(p)
+    assert coeffs.size == g.comp_coeffs[comp]
+    d_in = _dev(coeffs, np.int32)
+    pw, ph = g.padded[comp]
+    d_out = torch.empty(pw * ph, dtype=torch.int32, device="cuda")
+    scratch = torch.empty(max(g.scratch_bytes, 16), dtype=torch.uint8, device="cuda")
+    capi.check("vc2b_idwt_raw",
+               capi.lib().vc2b_idwt_raw(C.byref(p), comp, _ptr(d_in), _ptr(d_out), _ptr(scratch),
+                                        scratch.numel(), _stream()))
+    return d_out.cpu().numpy().reshape(ph, pw)
+
+
+def dwt_component(p, comp, padded_picture):
+    """dwt (pseudocode/picture_encoding.py:93) of one component: int32 [padded_h, padded_w] ->
+    flat int32 coefficients in subband order."""
+    torch = _torch()
+    g = Geometry(p)
+    pw, ph = g.padded[comp]
+    assert padded_picture.shape == (ph, pw)
+    d_in = _dev(padded_picture, np.int32)
+    d_out = torch.empty(g.comp_coeffs[comp], dtype=torch.int32, device="cuda")
+    scratch = torch.empty(max(g.scratch_bytes, 16), dtype=torch.uint8, device="cuda")
+    capi.check("vc2b_dwt_raw",
+               capi.lib().vc2b_dwt_raw(C.byref(p), comp, _ptr(d_in), _ptr(d_out), _ptr(scratch),
+                                       scratch.numel(), _stream()))
+    return d_out.cpu().numpy()
+
+
+def inverse_quant(values, quant_indices):
+    torch = _torch()
+    v = _dev(values, np.int32)
+    q = _dev(np.broadcast_to(quant_indices, np.shape(values)), np.int32)
+    out = torch.empty_like(v)
+    capi.check("vc2b_inverse_quant",
+               capi.lib().vc2b_inverse_quant(_ptr(v), _ptr(q), _ptr(out), v.numel(), _stream()))
+    return out.cpu().numpy()
+
+
+def forward_quant(values, quant_indices):
+    torch = _torch()
+    v = _dev(values, np.int32)
+    q = _dev(np.broadcast_to(quant_indices, np.shape(values)), np.int32)
+    out = torch.empty_like(v)
+    capi.check("vc2b_forward_quant",
+               capi.lib().vc2b_forward_quant(_ptr(v), _ptr(q), _ptr(out), v.numel(), _stream()))
+    return out.cpu().numpy()
+
+
+CLIP = 1
+ADD_OFFSET = 2
+REMOVE_OFFSET = 4
+
+
+def clip_offset(values, depth, mode):
+    v = _dev(values, np.int32)
+    capi.check("vc2b_clip_offset", capi.lib().vc2b_clip_offset(_ptr(v), v.numel(), int(depth), int(mode), _stream()))
+    return v.cpu().numpy()
+
+
+def dc_prediction(p, picture_coeffs, inverse=False):
+    """dc_prediction (decoder/transform_data_syntax.py:63) or its inverse apply_dc_prediction
+    (encoder/pictures.py:202) on the level-0 bands of one picture's flat coefficients."""
+    v = _dev(picture_coeffs, np.int32)
+    capi.check("vc2b_dc_prediction",
+               capi.lib().vc2b_dc_prediction(C.byref(p), _ptr(v), 1, 1 if inverse else 0, _stream()))
+    return v.cpu().numpy()
