@@ -78,6 +78,10 @@ int64_t vc2b_picture_coeff_count(const vc2b_params *p);
 /* Padded (transform) dimensions and decoded sample count of a picture (Y,C1,C2 planes). */
 int vc2b_padded_dims(const vc2b_params *p, int comp, int32_t *width, int32_t *height);
 int64_t vc2b_picture_sample_count(const vc2b_params *p);
+/* Largest |coefficient| for which the int32 inverse transform provably cannot overflow (the
+ * bound propagates magnitudes through every lifting stage).  vc2b_unpack reports
+ * VC2B_ST_INT32_ENVELOPE for a picture whose largest decoded coefficient exceeds it. */
+int64_t vc2b_idwt_max_safe_coeff(const vc2b_params *p);
 /* Bytes of scratch one picture needs in vc2b_idwt / vc2b_dwt (intermediate LL bands). */
 int64_t vc2b_transform_scratch_bytes(const vc2b_params *p);
 

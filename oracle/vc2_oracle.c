@@ -964,6 +964,10 @@ int64_t vc2o_encode_hq_lossy(const vc2o_params *p, const int64_t *cy, const int6
             len[0] = ceil_div(vc2o_calculate_coeffs_bits(sb.q[0], sb.n[0]), 8 * scaler);
             len[1] = ceil_div(vc2o_calculate_coeffs_bits(sb.q[1], sb.n[1]), 8 * scaler);
             len[2] = total_length - len[0] - len[1];
+            if (len[0] > 255 || len[1] > 255 || len[2] > 255 || qindex > 255) {
+                slicebuf_free(&sb); /* bitstream/io.py:485 OutOfRangeError: scaler too small */
+                return -2;
+            }
             if (qindex_out) qindex_out[n] = qindex;
             write_hq_slice(p, &w, &sb, qindex, len);
         }

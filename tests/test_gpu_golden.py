@@ -41,6 +41,9 @@ def test_decode_golden_pictures(name):
 def test_decode_corrupt_streams(name):
     """Dangling / truncated bounded blocks, garbage lengths, end of stream
     (vc2_conformance/test_cases/decoder/pictures.py:351-472 semantics)."""
+    import ctypes as C
+
+    from vc2_conformance_b200 import capi
     from vc2_conformance_b200.device import BatchCodec
 
     z = load("pictures")
@@ -50,7 +53,15 @@ def test_decode_corrupt_streams(name):
         bdata = z[v + ".data"].tobytes()
         codec.decode_streams([bdata], check=False)
         st = codec.status_host(1)[0]
-        assert st[0] == int(z[v + ".status"][0]), (v, st)
+        exp_status = int(z[v + ".status"][0])
+        if st[0] == capi.ST_INT32_ENVELOPE and exp_status == 0:
+            # The reference computes in unbounded integers; the CUDA path must flag (not wrap)
+            # a picture whose coefficients leave its documented int32 envelope.
+            safe = capi.lib().vc2b_idwt_max_safe_coeff(C.byref(p))
+            biggest = max(int(np.abs(z[v + ".dec_coeffs%d" % c]).max()) for c in range(3))
+            assert biggest > safe, (v, biggest, safe)
+            continue
+        assert st[0] == exp_status, (v, st)
         if st[0] == 0:
             assert st[2] == int(z[v + ".consumed"][0]), v
             coeffs = codec.coeff_components(0)

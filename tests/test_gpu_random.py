@@ -1,0 +1,228 @@
+"""CUDA path against the C oracle on seeded random inputs (sizes the oracle finishes in seconds),
+plus size-independent properties at the BASELINE.json sizes."""
+
+import numpy as np
+import pytest
+
+import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(**kw):
+    from vc2_conformance_b200.params import make_params
+
+    kw.setdefault("quant_matrix", synth.default_quant_matrix(kw.get("dwt_depth", 3), kw.get("dwt_depth_ho", 0)))
+    return make_params(**kw)
+
+
+def _oracle_streams(p, pictures, picture_bytes_list):
+    import oracle as O
+
+    po = synth.oracle_params(p)
+    streams, decoded = [], []
+    for planes, pb in zip(pictures, picture_bytes_list):
+        coeffs = O.encode_picture(po, planes)
+        if p.is_ld:
+            data, q = O.encode_ld_lossy(po, coeffs)
+        elif pb is None:
+            data = O.encode_hq_fixed(po, coeffs, 0)
+        else:
+            data, q = O.encode_hq_lossy(po, coeffs, pb)
+        st, out, consumed = O.decode_picture(po, data)
+        assert st == 0 and consumed == len(data)
+        streams.append(data)
+        decoded.append(out)
+    return streams, decoded
+
+
+HQ_CASES = [
+    # W, H, cw, ch, depth, wi, wiho, d, dho, sx, sy, scaler
+    (320, 192, 160, 192, 10, 0, 0, 3, 0, 10, 12, 1),
+    (352, 288, 176, 144, 8, 1, 1, 3, 0, 11, 9, 1),
+    (256, 128, 256, 128, 12, 5, 6, 2, 3, 2, 8, 2),
+    (200, 120, 100, 120, 10, 2, 2, 2, 0, 7, 5, 1),
+    (192, 96, 96, 96, 16, 6, 6, 2, 1, 6, 6, 3),
+    (128, 64, 64, 64, 10, 4, 3, 1, 1, 4, 4, 1),
+]
+
+
+@pytest.mark.parametrize("case", HQ_CASES)
+def test_hq_batch_vs_oracle(case):
+    from vc2_conformance_b200.device import BatchCodec
+
+    import oracle as O
+
+    W, H, cw, ch, depth, wi, wiho, d, dho, sx, sy, scaler = case
+    S = W * H + 2 * cw * ch
+    # scaler large enough for the biggest picture_bytes used below (encoder/pictures.py:586)
+    scaler = max(scaler, O.safe_lossy_hq_slice_size_scaler(2 * S, sx * sy))
+    p = _mk(luma_width=W, luma_height=H, color_diff_width=cw, color_diff_height=ch, luma_depth=depth,
+            wavelet_index=wi, wavelet_index_ho=wiho, dwt_depth=d, dwt_depth_ho=dho, slices_x=sx, slices_y=sy,
+            slice_size_scaler=scaler)
+    S = W * H + 2 * cw * ch
+    pics = [synth.noise_picture(p, 0), synth.ramp_picture(p, 1), synth.noise_picture(p, 2),
+            synth.ramp_picture(p, 3), synth.noise_picture(p, 4)]
+    # ~2 bits/sample, ~6 bits/sample, nearly lossless sizes
+    pbs = [S // 4, S // 2, S, S // 3, S * 2]
+    streams, decoded = _oracle_streams(p, pics, pbs)
+    codec = BatchCodec(p, len(pics))
+    codec.decode_streams(streams)
+    for i in range(len(pics)):
+        planes = codec.picture_planes(i)
+        for c in range(3):
+            assert (planes[c] == decoded[i][c]).all(), (case, i, c)
+    # encoder mirror on the same pictures: bytes identical to the oracle's
+    flat = np.stack([synth.flat_picture(pl) for pl in pics])
+    for i, pb in enumerate(pbs):
+        out = codec.encode_pictures(flat[i:i + 1], pb)
+        assert out[0] == streams[i], (case, i)
+
+
+LD_CASES = [
+    (320, 192, 160, 192, 10, 4, 4, 2, 0, 10, 12, 5, 1),
+    (128, 128, 64, 64, 8, 1, 1, 3, 0, 4, 8, 3, 1),
+    (192, 64, 192, 64, 12, 3, 3, 1, 2, 6, 4, 7, 2),
+    (96, 80, 48, 80, 10, 0, 0, 2, 0, 3, 5, 9, 4),
+]
+
+
+@pytest.mark.parametrize("case", LD_CASES)
+def test_ld_batch_vs_oracle(case):
+    from vc2_conformance_b200.device import BatchCodec
+    from vc2_conformance_b200.params import copy_params
+
+    W, H, cw, ch, depth, wi, wiho, d, dho, sx, sy, num, den = case
+    S = W * H + 2 * cw * ch
+    # bytes per picture = num/den of the raw size
+    pbytes = (S * depth // 8) * den // (num * 2) * 2
+    p = _mk(luma_width=W, luma_height=H, color_diff_width=cw, color_diff_height=ch, luma_depth=depth,
+            wavelet_index=wi, wavelet_index_ho=wiho, dwt_depth=d, dwt_depth_ho=dho, slices_x=sx, slices_y=sy,
+            is_ld=True, slice_bytes_numerator=pbytes, slice_bytes_denominator=sx * sy)
+    pics = [synth.noise_picture(p, 10), synth.ramp_picture(p, 11), synth.ramp_picture(p, 12)]
+    streams, decoded = _oracle_streams(p, pics, [None] * 3)
+    codec = BatchCodec(p, len(pics))
+    codec.decode_streams(streams)
+    for i in range(len(pics)):
+        planes = codec.picture_planes(i)
+        for c in range(3):
+            assert (planes[c] == decoded[i][c]).all(), (case, i, c)
+    flat = np.stack([synth.flat_picture(pl) for pl in pics])
+    out = codec.encode_pictures(flat, 0)
+    for i in range(len(pics)):
+        assert out[i] == streams[i], (case, i)
+
+
+@pytest.mark.parametrize("wi", range(7))
+@pytest.mark.parametrize("wiho,d,dho", [(None, 3, 0), (1, 2, 1), (6, 1, 2), (5, 0, 2), (0, 2, 2)])
+def test_transforms_vs_oracle(wi, wiho, d, dho):
+    import oracle as O
+    from vc2_conformance_b200 import ops
+
+    wiho = wi if wiho is None else wiho
+    W, H = 360, 136  # padded by the transform for most depths
+    p = _mk(luma_width=W, luma_height=H, wavelet_index=wi, wavelet_index_ho=wiho, dwt_depth=d, dwt_depth_ho=dho)
+    po = synth.oracle_params(p)
+    pw, ph = O.padded_dims(po, 0)
+    rng = np.random.RandomState(wi * 31 + d * 7 + dho)
+    coeffs = rng.randint(-900, 900, pw * ph).astype(np.int32)
+    assert (ops.idwt_component(p, 0, coeffs) == O.idwt(po, 0, coeffs.astype(np.int64))).all()
+    pic = rng.randint(-2048, 2048, (ph, pw)).astype(np.int32)
+    got = ops.dwt_component(p, 0, pic)
+    assert (got == O.dwt(po, 0, pic.astype(np.int64))).all()
+    # dwt o idwt identity (tests/pseudocode/test_picture_encoding.py:113-142)
+    assert (ops.idwt_component(p, 0, got) == pic).all()
+
+
+def test_elementwise_vs_oracle():
+    import oracle as O
+    from vc2_conformance_b200 import ops
+
+    rng = np.random.RandomState(5)
+    v = rng.randint(-(1 << 17), 1 << 17, 5000).astype(np.int32)
+    qi = rng.randint(0, 40, 5000).astype(np.int32)
+    L = O.lib()
+    exp = np.array([L.vc2o_inverse_quant(int(a), int(b)) for a, b in zip(v, qi)])
+    ok = np.abs(exp) < (1 << 31)
+    assert (ops.inverse_quant(v, qi)[ok] == exp[ok]).all()
+    exp = np.array([L.vc2o_forward_quant(int(a), int(b)) for a, b in zip(v, qi)])
+    assert (ops.forward_quant(v, qi) == exp).all()
+    x = rng.randint(-3000, 3000, 4000).astype(np.int32)
+    assert (ops.clip_offset(x, 10, ops.CLIP | ops.ADD_OFFSET) == np.clip(x, -512, 511) + 512).all()
+    assert (ops.clip_offset(x, 10, ops.REMOVE_OFFSET) == x - 512).all()
+
+
+FULL_CASES = [
+    # BASELINE.json configs at full size: (name, params kwargs, picture_bytes or None)
+    ("cfg1_1080p_legall_d3_8x8", dict(luma_width=1920, luma_height=1080, color_diff_width=960,
+                                      color_diff_height=1080, luma_depth=10, wavelet_index=1, dwt_depth=3,
+                                      slices_x=8, slices_y=8, slice_size_scaler=1024)),
+    ("cfg1_1080p_legall_d3_60x135", dict(luma_width=1920, luma_height=1080, color_diff_width=960,
+                                         color_diff_height=1080, luma_depth=10, wavelet_index=1, dwt_depth=3,
+                                         slices_x=60, slices_y=135, slice_size_scaler=8)),
+    ("cfg2_2160p_dd97_d4", dict(luma_width=3840, luma_height=2160, color_diff_width=1920,
+                                color_diff_height=2160, luma_depth=10, wavelet_index=0, dwt_depth=4,
+                                slices_x=120, slices_y=135, slice_size_scaler=16)),
+    ("cfg4_1080p_fidelity_daub_444", dict(luma_width=1920, luma_height=1080, luma_depth=12, wavelet_index=5,
+                                          wavelet_index_ho=6, dwt_depth=2, dwt_depth_ho=3, slices_x=60,
+                                          slices_y=270, slice_size_scaler=8)),
+]
+
+
+@pytest.mark.parametrize("name,kw", FULL_CASES)
+def test_full_size_roundtrip_and_oracle(name, kw):
+    """At full size: (1) lossless encode -> decode is the identity on device (round trip through
+    DWT, qindex search, packing, slice index, unpack, IDWT); (2) a lossy stream decodes to exactly
+    the oracle's picture; (3) the device encoder emits the oracle's bytes."""
+    import oracle as O
+    from vc2_conformance_b200.device import BatchCodec
+
+    p = _mk(**kw)
+    po = synth.oracle_params(p)
+    ns = p.slices_x * p.slices_y
+    S = p.luma_width * p.luma_height + 2 * p.color_diff_width * p.color_diff_height
+    codec = BatchCodec(p, 2, max_stream_bytes=4 * S)
+    pics = [synth.noise_picture(p, 0), synth.ramp_picture(p, 1)]
+    flat = np.stack([synth.flat_picture(pl) for pl in pics])
+    # (1) room for everything at qindex 0
+    big = ns * (4 + 255 * p.slice_size_scaler)
+    streams = codec.encode_pictures(flat, big)
+    assert (codec.qindex[: 2 * ns].cpu().numpy() == 0).all()
+    out = codec.decode_streams(streams).cpu().numpy()
+    assert (out == flat).all()
+    # (2)+(3) lossy at ~2.5 bits/sample against the oracle
+    pb = (S * 5 // 16) // 4 * 4
+    coeffs = O.encode_picture(po, pics[0])
+    data, q = O.encode_hq_lossy(po, coeffs, pb)
+    st, dec, consumed = O.decode_picture(po, data)
+    assert st == 0
+    got = codec.decode_streams([data])
+    planes = codec.picture_planes(0)
+    for c in range(3):
+        assert (planes[c] == dec[c]).all(), (name, c)
+    enc = codec.encode_pictures(flat[0:1], pb)
+    assert enc[0] == data
+
+
+def test_full_size_ld_field():
+    """BASELINE config 3: 1080i LD field, Haar-with-shift depth 2, 60x135 slices, 4:1."""
+    import oracle as O
+    from vc2_conformance_b200.device import BatchCodec
+
+    S = 1920 * 540 + 2 * 960 * 540
+    pbytes = S * 10 // 8 // 4
+    p = _mk(luma_width=1920, luma_height=540, color_diff_width=960, color_diff_height=540, luma_depth=10,
+            wavelet_index=4, dwt_depth=2, slices_x=60, slices_y=135, is_ld=True,
+            slice_bytes_numerator=pbytes, slice_bytes_denominator=60 * 135)
+    po = synth.oracle_params(p)
+    pics = [synth.ramp_picture(p, 3), synth.noise_picture(p, 4)]
+    streams, decoded = _oracle_streams(p, pics, [None, None])
+    codec = BatchCodec(p, 2)
+    codec.decode_streams(streams)
+    for i in range(2):
+        planes = codec.picture_planes(i)
+        for c in range(3):
+            assert (planes[c] == decoded[i][c]).all(), (i, c)
+    flat = np.stack([synth.flat_picture(pl) for pl in pics])
+    out = codec.encode_pictures(flat, 0)
+    assert out[0] == streams[0] and out[1] == streams[1]

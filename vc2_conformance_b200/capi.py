@@ -77,6 +77,7 @@ SIGNATURES = {
     "vc2b_padded_dims": (_i, [_PP, _i, _vp, _vp]),
     "vc2b_picture_sample_count": (_i64, [_PP]),
     "vc2b_transform_scratch_bytes": (_i64, [_PP]),
+    "vc2b_idwt_max_safe_coeff": (_i64, [_PP]),
     "vc2b_hq_slice_offsets": (_i, [_PP, _vp, _vp, _i, _vp, _vp, _vp]),
     "vc2b_unpack": (_i, [_PP, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "vc2b_dc_prediction": (_i, [_PP, _vp, _i, _i, _vp]),

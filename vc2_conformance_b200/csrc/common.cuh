@@ -46,6 +46,10 @@ struct DevParams {
 
 // Builds DevParams; returns 0 or VC2B_E_*.
 int make_dev_params(const vc2b_params *p, DevParams *d);
+// Largest |coefficient| for which the int32 synthesis provably cannot overflow (params.cu).
+long long idwt_max_safe_coeff(const vc2b_params *p);
+// Whether the int32 analysis of samples of the given depth provably cannot overflow.
+bool dwt_is_safe(const vc2b_params *p);
 
 __host__ __device__ inline int32_t ilog2_ceil(int64_t n)
 {

@@ -298,6 +298,7 @@ int vc2b_dwt(const vc2b_params *p, const uint16_t *d_pictures, int npictures, in
     int st = make_dev_params(p, &P);
     if (st) return st;
     if (npictures <= 0) return 0;
+    if (!dwt_is_safe(p)) return VC2B_E_UNSUPPORTED;  // outside the int32 envelope
     AnaScratch sp;
     plan_ana_scratch(P, 0, 3, &sp);
     const long long per_pic = (sp.size_a + sp.size_b) * (long long)sizeof(int32_t);

@@ -2,7 +2,7 @@
 //
 // Restates pseudocode/slice_sizes.py:53-92 (subband_width / subband_height) and
 // the subband ordering of decoder/transform_data_syntax.py:176-189,230-243.
-#include "common.cuh"
+#include "lifting.cuh"
 
 namespace vc2b {
 
@@ -96,6 +96,128 @@ int make_dev_params(const vc2b_params *p, DevParams *d)
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// int32 envelope of the transforms.  The reference computes in unbounded integers; the kernels
+// hold samples in int32 (accumulating in int64 only for the S >= 8 filters).  These bounds
+// propagate the largest possible magnitude through every level using the L-infinity operator
+// norms of the lifting passes and report the worst value that must fit 31 bits.
+// ---------------------------------------------------------------------------------------------
+struct PassGain {
+    double out;    // max abs row sum of the whole 1-D pass (L-infinity operator norm)
+    double worst;  // largest norm reached after any stage, or by an int32 accumulator
+};
+
+// Norms of the linear part of oned_synthesis / oned_analysis, measured on the actual lifting
+// operator (including the edge clamps) for several array lengths.
+static PassGain pass_gain(int filter, bool analysis)
+{
+    const FilterDef f = get_filter(filter);
+    PassGain g = {1.0, 1.0};
+    const int lens[5] = {2, 4, 8, 16, 64};
+    for (int li = 0; li < 5; li++) {
+        const int N = lens[li];
+        static double M[64][64];
+        for (int r = 0; r < N; r++)
+            for (int c = 0; c < N; c++) M[r][c] = r == c ? 1.0 : 0.0;
+        for (int k = 0; k < f.nstages; k++) {
+            const StageDef &st = f.st[analysis ? f.nstages - 1 - k : k];
+            const int type = analysis ? analysis_type(st.type) : st.type;
+            const bool even = (type == 1 || type == 2);
+            const double sign = (type == 1 || type == 3) ? 1.0 : -1.0;
+            for (int n = 0; n < N / 2; n++) {
+                double acc[64];
+                for (int c = 0; c < N; c++) acc[c] = 0.0;
+                for (int i = st.D; i < st.L + st.D; i++) {
+                    int pos = even ? 2 * (n + i) - 1 : 2 * (n + i);
+                    if (even) { if (pos > N - 1) pos = N - 1; if (pos < 1) pos = 1; }
+                    else { if (pos > N - 2) pos = N - 2; if (pos < 0) pos = 0; }
+                    for (int c = 0; c < N; c++) acc[c] += st.taps[i - st.D] * M[pos][c];
+                }
+                double accnorm = 0.0;
+                for (int c = 0; c < N; c++) accnorm += acc[c] < 0 ? -acc[c] : acc[c];
+                if (st.S < 8 && accnorm > g.worst) g.worst = accnorm;  // int32 accumulator
+                const int t = even ? 2 * n : 2 * n + 1;
+                double rown = 0.0;
+                for (int c = 0; c < N; c++) {
+                    M[t][c] += sign * acc[c] / (double)(1LL << st.S);
+                    rown += M[t][c] < 0 ? -M[t][c] : M[t][c];
+                }
+                if (rown > g.worst) g.worst = rown;
+                if (k == f.nstages - 1 && rown > g.out) g.out = rown;
+            }
+            if (k == f.nstages - 1) {  // rows the last stage did not touch
+                for (int r = 0; r < N; r++) {
+                    double rown = 0.0;
+                    for (int c = 0; c < N; c++) rown += M[r][c] < 0 ? -M[r][c] : M[r][c];
+                    if (rown > g.out) g.out = rown;
+                }
+            }
+        }
+    }
+    if (g.out > g.worst) g.worst = g.out;
+    return g;
+}
+
+// one 1-D pass over samples bounded by v: returns the new bound; rounding adds < 1 per stage,
+// amplified by at most the pass's worst norm
+static double apply_pass(const PassGain &g, double v, double *worst)
+{
+    const double slack = 4.0 * g.worst + 4.0;
+    if (g.worst * v + slack > *worst) *worst = g.worst * v + slack;
+    return g.out * v + slack;
+}
+
+// worst intermediate magnitude of the synthesis when every coefficient is bounded by m
+static double idwt_worst(const vc2b_params *p, double m)
+{
+    const PassGain gv = pass_gain(p->wavelet_index, false), gh = pass_gain(p->wavelet_index_ho, false);
+    double worst = m, ll = m;
+    const int shift = get_filter(p->wavelet_index_ho).shift;
+    const int top = p->dwt_depth + p->dwt_depth_ho;
+    for (int n = 1; n <= top; n++) {
+        double v = ll > m ? ll : m;
+        if (n > p->dwt_depth_ho) v = apply_pass(gv, v, &worst);
+        v = apply_pass(gh, v, &worst);
+        if (shift > 0) v = (v + (double)(1 << (shift - 1))) / (double)(1 << shift) + 1.0;
+        ll = v;
+    }
+    return worst;
+}
+
+// worst intermediate magnitude of the analysis of samples bounded by m
+static double dwt_worst(const vc2b_params *p, double m)
+{
+    const PassGain gv = pass_gain(p->wavelet_index, true), gh = pass_gain(p->wavelet_index_ho, true);
+    double worst = m, ll = m;
+    const int shift = get_filter(p->wavelet_index_ho).shift;
+    const int top = p->dwt_depth + p->dwt_depth_ho;
+    for (int n = top; n >= 1; n--) {
+        double v = ll * (double)(1 << shift);
+        if (v > worst) worst = v;
+        v = apply_pass(gh, v, &worst);
+        if (n > p->dwt_depth_ho) v = apply_pass(gv, v, &worst);
+        ll = v;
+    }
+    return worst;
+}
+
+long long idwt_max_safe_coeff(const vc2b_params *p)
+{
+    const double limit = 2147483647.0;
+    long long lo = 0, hi = 0x7fffffffLL;  // largest m with idwt_worst(m) <= limit
+    while (lo < hi) {
+        long long mid = (lo + hi + 1) >> 1;
+        if (idwt_worst(p, (double)mid) <= limit) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+bool dwt_is_safe(const vc2b_params *p)
+{
+    int depth = p->luma_depth > p->color_diff_depth ? p->luma_depth : p->color_diff_depth;
+    return dwt_worst(p, (double)(1LL << (depth - 1))) <= 2147483647.0;
+}
+
 }  // namespace vc2b
 
 using namespace vc2b;
@@ -158,6 +280,14 @@ int vc2b_padded_dims(const vc2b_params *p, int comp, int32_t *width, int32_t *he
     if (width) *width = d.pw[comp];
     if (height) *height = d.ph[comp];
     return 0;
+}
+
+int64_t vc2b_idwt_max_safe_coeff(const vc2b_params *p)
+{
+    DevParams d;
+    int st = make_dev_params(p, &d);
+    if (st) return st;
+    return idwt_max_safe_coeff(p);
 }
 
 int64_t vc2b_picture_sample_count(const vc2b_params *p)

@@ -447,6 +447,11 @@ int vc2b_quantize_to_fit(const vc2b_params *p, const int32_t *d_coeffs, int npic
     const long long nslices = (long long)P.slices_x * P.slices_y;
     F.total_coeff_bytes = picture_bytes - 4 * nslices;
     if (!P.is_ld && F.total_coeff_bytes < 0) return VC2B_E_BAD_PARAMS;  // InsufficientHQPictureBytesError
+    if (!P.is_ld) {
+        // every length field must fit 8 bits (get_safe_lossy_hq_slice_size_scaler, encoder/pictures.py:586)
+        const long long den = nslices * P.slice_size_scaler;
+        if ((F.total_coeff_bytes + den - 1) / den > 255) return VC2B_E_BAD_PARAMS;
+    }
     F.minimum_qindex = minimum_qindex < 0 ? 0 : minimum_qindex;
     F.max_qm = max_qm(P);
     const long long warps = npictures * nslices;

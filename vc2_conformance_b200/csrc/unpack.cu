@@ -135,13 +135,15 @@ __global__ void ld_init_status_kernel(DevParams P, const int64_t *__restrict__ p
 
 // status[0] is kept as an atomicMin key (slice*8 + code) while kernels run; this turns it
 // into {status, first bad slice}.
-__global__ void finalize_status_kernel(int npictures, int32_t *__restrict__ status)
+__global__ void finalize_status_kernel(int npictures, int32_t *__restrict__ status, int max_safe_coeff)
 {
     int pic = blockIdx.x * blockDim.x + threadIdx.x;
     if (pic >= npictures) return;
     int key = status[4 * pic + 0];
     if (key == kErrOk) {
-        status[4 * pic + 0] = VC2B_ST_OK;
+        // a value left the int32 envelope (the reference, in unbounded integers, would carry on):
+        // reported only when the stream has no error the reference itself would raise
+        status[4 * pic + 0] = (status[4 * pic + 3] > max_safe_coeff) ? VC2B_ST_INT32_ENVELOPE : VC2B_ST_OK;
         status[4 * pic + 1] = -1;
     } else {
         status[4 * pic + 0] = key & 7;
@@ -441,8 +443,7 @@ unpack_hq_kernel(DevParams P, const uint8_t *__restrict__ data, const int64_t *_
         pos += length;
     }
     if (lane == 0) {
-        if (bad) report(status, pic, n, VC2B_ST_INT32_ENVELOPE);
-        atomicMax(&status[4 * pic + 3], maxabs);
+        atomicMax(&status[4 * pic + 3], bad ? 0x7fffffff : maxabs);
     }
 }
 
@@ -500,8 +501,7 @@ unpack_ld_kernel(DevParams P, const uint8_t *__restrict__ data, const int64_t *_
                            pc + P.comp_off[1], pc + P.comp_off[2], lut, lane);
     if (m < 0) bad = true; else maxabs = max(maxabs, m);
     if (lane == 0) {
-        if (bad) report(status, pic, n, VC2B_ST_INT32_ENVELOPE);
-        atomicMax(&status[4 * pic + 3], maxabs);
+        atomicMax(&status[4 * pic + 3], bad ? 0x7fffffff : maxabs);
     }
 }
 
@@ -514,14 +514,27 @@ unpack_ld_kernel(DevParams P, const uint8_t *__restrict__ data, const int64_t *_
 // ---------------------------------------------------------------------------
 constexpr int kDcThreads = 256;
 
-__device__ __forceinline__ int floordiv3(int v)
+__device__ __forceinline__ long long floordiv3(long long v)
 {
-    int q = v / 3;
+    long long q = v / 3;
     return (v - q * 3 < 0) ? q - 1 : q;
 }
 
+__device__ __forceinline__ int narrow_or_flag(long long v, int32_t *status_word)
+{
+    if (v > 0x7fffffffLL || v < -0x7fffffffLL) {  // left the int32 envelope
+        if (status_word) atomicMax(status_word, 0x7fffffff);
+        return 0;
+    }
+    if (status_word) {
+        const int a = (int)(v < 0 ? -v : v);
+        if (a > *status_word) atomicMax(status_word, a);
+    }
+    return (int)v;
+}
+
 __global__ void __launch_bounds__(kDcThreads)
-dc_prediction_kernel(DevParams P, int32_t *__restrict__ coeffs, int inverse)
+dc_prediction_kernel(DevParams P, int32_t *__restrict__ coeffs, int inverse, int32_t *__restrict__ status)
 {
     __shared__ int32_t up[2][kDcThreads + 1];
     const int pic = blockIdx.x / 3, comp = blockIdx.x % 3;
@@ -529,6 +542,7 @@ dc_prediction_kernel(DevParams P, int32_t *__restrict__ coeffs, int inverse)
     const int w = B.w, h = B.h;
     int32_t *band = coeffs + (size_t)pic * P.pic_coeffs + P.comp_off[comp] + B.off;
     const int t = threadIdx.x;
+    int32_t *sw = status ? &status[4 * pic + 3] : nullptr;  // running max |coefficient|
 
     if (!inverse) {
         // forward recurrence: strips of rows top to bottom, values final in global memory
@@ -544,12 +558,12 @@ dc_prediction_kernel(DevParams P, int32_t *__restrict__ coeffs, int inverse)
                 if (active && x >= 0 && x < w) {
                     int upv = 0;
                     if (y > 0) upv = (t == 0) ? band[(size_t)(y - 1) * w + x] : up[(step + 1) & 1][t];
-                    int pred;
-                    if (x > 0 && y > 0) pred = floordiv3(left + upleft + upv + 1);
+                    long long pred;
+                    if (x > 0 && y > 0) pred = floordiv3((long long)left + upleft + upv + 1);
                     else if (x > 0) pred = left;
                     else if (y > 0) pred = upv;
                     else pred = 0;
-                    value = band[(size_t)y * w + x] + pred;
+                    value = narrow_or_flag((long long)band[(size_t)y * w + x] + pred, sw);
                     band[(size_t)y * w + x] = value;
                     left = value;
                     upleft = upv;
@@ -579,12 +593,13 @@ dc_prediction_kernel(DevParams P, int32_t *__restrict__ coeffs, int inverse)
                     int ty = i / TC + 1, tx = i - (ty - 1) * TC + 1;
                     int y = y0 - 1 + ty, x = x0 - 1 + tx;
                     if (y < h && x < w) {
-                        int pred;
-                        if (x > 0 && y > 0) pred = floordiv3(tile[ty][tx - 1] + tile[ty - 1][tx - 1] + tile[ty - 1][tx] + 1);
+                        long long pred;
+                        if (x > 0 && y > 0)
+                            pred = floordiv3((long long)tile[ty][tx - 1] + tile[ty - 1][tx - 1] + tile[ty - 1][tx] + 1);
                         else if (x > 0) pred = tile[ty][tx - 1];
                         else if (y > 0) pred = tile[ty - 1][tx];
                         else pred = 0;
-                        band[(size_t)y * w + x] = tile[ty][tx] - pred;
+                        band[(size_t)y * w + x] = narrow_or_flag((long long)tile[ty][tx] - pred, sw);
                     }
                 }
                 __syncthreads();
@@ -619,7 +634,7 @@ int vc2b_dc_prediction(const vc2b_params *p, int32_t *d_coeffs, int npictures, i
     int st = make_dev_params(p, &P);
     if (st) return st;
     if (npictures <= 0) return 0;
-    dc_prediction_kernel<<<npictures * 3, kDcThreads, 0, (cudaStream_t)stream>>>(P, d_coeffs, inverse);
+    dc_prediction_kernel<<<npictures * 3, kDcThreads, 0, (cudaStream_t)stream>>>(P, d_coeffs, inverse, nullptr);
     VC2B_CHECK_LAUNCH();
     return 0;
 }
@@ -642,7 +657,7 @@ int vc2b_unpack(const vc2b_params *p, const uint8_t *d_data, const int64_t *d_pi
                                                                 d_qindex, d_status);
         VC2B_CHECK_LAUNCH();
         // using_dc_prediction (pseudocode/parse_code_functions.py:70): LD pictures only
-        dc_prediction_kernel<<<npictures * 3, kDcThreads, 0, s>>>(P, d_coeffs, 0);
+        dc_prediction_kernel<<<npictures * 3, kDcThreads, 0, s>>>(P, d_coeffs, 0, d_status);
         VC2B_CHECK_LAUNCH();
     } else {
         if (!d_slice_offset) return VC2B_E_BAD_PARAMS;
@@ -650,7 +665,9 @@ int vc2b_unpack(const vc2b_params *p, const uint8_t *d_data, const int64_t *d_pi
                                                                 d_slice_offset, d_coeffs, d_qindex, d_status);
         VC2B_CHECK_LAUNCH();
     }
-    finalize_status_kernel<<<(npictures + 127) / 128, 128, 0, s>>>(npictures, d_status);
+    long long safe = idwt_max_safe_coeff(p);
+    if (safe > 0x7ffffffeLL) safe = 0x7ffffffeLL;  // 0x7fffffff marks a value that did not fit int32
+    finalize_status_kernel<<<(npictures + 127) / 128, 128, 0, s>>>(npictures, d_status, (int)safe);
     VC2B_CHECK_LAUNCH();
     return 0;
 }

@@ -15,7 +15,7 @@ from .params import Geometry
 
 def _dev(a, dtype):
     torch = _torch()
-    a = np.ascontiguousarray(a, dtype)
+    a = np.array(a, dtype=dtype, order="C", copy=True)
     if dtype == np.uint16:
         return torch.from_numpy(a.view(np.int16)).cuda().view(torch.uint16)
     return torch.from_numpy(a).cuda()
