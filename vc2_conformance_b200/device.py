@@ -238,3 +238,80 @@ class _null(object):
 
     def __exit__(self, *a):
         return False
+
+
+class SequenceDecoder(object):
+    """End-to-end decode of a whole sequence held in HOST memory: the pictures' transform data
+    goes host -> device, is decoded, and the pictures come back device -> host, in chunks
+    pipelined over several CUDA streams so copies overlap kernels.
+
+    This is the throughput form of the per-picture entry points the reference calls in
+    decoder/stream.py:128-133 (picture_parse's transform_data, then picture_decode)."""
+
+    def __init__(self, params, chunk=8, nstreams=3, max_chunk_bytes=1 << 20, device="cuda:0"):
+        torch = _torch()
+        self.torch = torch
+        self.p = params
+        self.chunk = int(chunk)
+        self.device = torch.device(device)
+        with torch.cuda.device(self.device):
+            self.streams = [torch.cuda.Stream(device=self.device) for _ in range(nstreams)]
+            self.codecs = [BatchCodec(params, self.chunk, max_chunk_bytes, device, group=self.chunk)
+                           for _ in range(nstreams)]
+        self.g = self.codecs[0].g
+
+    @property
+    def launches(self):
+        return sum(c.launches for c in self.codecs)
+
+    def plan(self, host_bytes, offsets):
+        """Pre-computes per-chunk views for a packed host buffer (pinned uint8 tensor with PAD
+        bytes of slack) and its [n+1] byte offsets."""
+        torch = self.torch
+        offsets = np.asarray(offsets, np.int64)
+        n = len(offsets) - 1
+        chunks = []
+        for i0 in range(0, n, self.chunk):
+            i1 = min(n, i0 + self.chunk)
+            b0, b1 = int(offsets[i0]), int(offsets[i1])
+            b0a = b0 & ~15  # keep 16-byte alignment of the device copy
+            rel = torch.from_numpy(offsets[i0:i1 + 1] - b0a).pin_memory()
+            chunks.append((i0, i1 - i0, host_bytes[b0a:b1 + PAD], rel))
+        return chunks
+
+    def decode(self, chunks, out_host):
+        """Enqueue the whole sequence; ``out_host`` is a pinned uint16 tensor
+        [n, picture_samples] receiving the decoded pictures.  Returns after enqueueing; call
+        ``synchronize()`` before reading ``out_host``."""
+        torch = self.torch
+        S = self.g.picture_samples
+        ns = len(self.streams)
+        for k, (i0, n, hbytes, rel) in enumerate(chunks):
+            s = self.streams[k % ns]
+            codec = self.codecs[k % ns]
+            codec.decode_host(hbytes, rel, n, s)
+            with torch.cuda.stream(s):
+                out_host[i0:i0 + n].copy_(codec.pictures[: n * S].view(n, S), non_blocking=True)
+
+    def fork_from(self, stream):
+        """Make every worker stream wait for ``stream`` (start of a timed region)."""
+        torch = self.torch
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        for s in self.streams:
+            s.wait_event(ev)
+
+    def join_to(self, stream):
+        """Make ``stream`` wait for every worker stream (end of a timed region)."""
+        torch = self.torch
+        for s in self.streams:
+            ev = torch.cuda.Event()
+            ev.record(s)
+            stream.wait_event(ev)
+
+    def synchronize(self):
+        for s in self.streams:
+            s.synchronize()
+
+    def statuses(self):
+        return [c.status_host(self.chunk) for c in self.codecs]
