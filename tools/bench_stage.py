@@ -1,0 +1,57 @@
+"""Stage micro-benchmarks (device timed): python tools/bench_stage.py idwt|dwt|unpack [--workload cfg2] [--pictures 16]"""
+import argparse, os, sys, ctypes as C
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+import numpy as np, torch
+import bench
+from vc2_conformance_b200 import capi
+from vc2_conformance_b200.device import BatchCodec, _ptr
+
+ap = argparse.ArgumentParser()
+ap.add_argument("stage")
+ap.add_argument("--workload", default="cfg2")
+ap.add_argument("--pictures", type=int, default=16)
+ap.add_argument("--group", type=int, default=4)
+ap.add_argument("--iters", type=int, default=10)
+a = ap.parse_args()
+w = bench.make_workload(a.workload, a.pictures)
+p, NP, S = w["p"], w["pictures"], w["samples"]
+codec = BatchCodec(p, NP, max_stream_bytes=NP * (w["picture_bytes"] + 64), group=a.group)
+pics = bench.synth_pictures(w, 0, min(NP, 4))
+streams = codec.encode_pictures(pics, w["picture_bytes"])
+streams = [streams[i % len(streams)] for i in range(NP)]
+host, offs = codec.pack_host_streams(streams)
+codec.decode_host(host, offs, NP)
+torch.cuda.synchronize()
+assert (codec.status_host(NP)[:, 0] == 0).all()
+L = codec.lib
+sp = codec._stream_ptr(None)
+padded = sum(codec.g.comp_coeffs)
+
+def run_idwt():
+    codec.idwt_device(NP)
+def run_dwt():
+    codec.dwt_device(NP)
+def run_unpack():
+    if not p.is_ld:
+        L.vc2b_hq_slice_offsets(C.byref(p), _ptr(codec.data), _ptr(codec.pic_offset), NP, _ptr(codec.slice_offset), _ptr(codec.status), sp)
+    L.vc2b_unpack(C.byref(p), _ptr(codec.data), _ptr(codec.pic_offset), NP, _ptr(codec.slice_offset), _ptr(codec.coeffs), _ptr(codec.qindex), _ptr(codec.status), sp)
+def run_walk():
+    L.vc2b_hq_slice_offsets(C.byref(p), _ptr(codec.data), _ptr(codec.pic_offset), NP, _ptr(codec.slice_offset), _ptr(codec.status), sp)
+def run_quant():
+    codec.quantize_device(NP, w["picture_bytes"])
+fn = {"idwt": run_idwt, "dwt": run_dwt, "unpack": run_unpack, "walk": run_walk, "quant": run_quant}[a.stage]
+nbytes = {"idwt": (4 * padded + 2 * S) * NP, "dwt": (4 * padded + 2 * S) * NP,
+          "unpack": int(offs[NP]) + 4 * padded * NP, "walk": int(offs[NP]), "quant": 4 * padded * NP}[a.stage]
+for _ in range(3):
+    fn()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(a.iters):
+    fn()
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / a.iters
+print("%s %s: %.3f ms per %d pictures = %.1f us/picture, %.1f GB/s algorithmic (%.1f%% of 6542)" % (
+    a.stage, a.workload, ms, NP, 1000 * ms / NP, nbytes / ms / 1e6, 100 * nbytes / ms / 1e6 / 6542.4))

@@ -5,18 +5,24 @@
 // oned_synthesis / filter_bit_shift / lift1-4 / idwt_pad_removal / clip_picture /
 // offset_picture (pseudocode/picture_decoding.py:45-349).
 //
-// One kernel launch per transform level, covering all three components and a group of
-// pictures (grid = tiles x components x pictures).  A CTA owns a TW x TH tile of the level's
-// OUTPUT, stages tile + halo of the four interleaved subbands in shared memory
-// (vh_synthesis :164-169), lifts columns with wavelet_index then rows with wavelet_index_ho
-// (:172-175), applies the level's rounding shift (:177-182, shift taken from wavelet_index_ho
-// :198-201) and writes either the next level's LL band (int32) or -- on the last level -- the
-// cropped, clipped, offset uint16 picture.
+// Design (B200): the stage is HBM-bound only if the lifting itself is nearly free, so the
+// lifting lives entirely in REGISTERS.  One launch per transform level covers all three
+// components and a group of pictures.  A WARP owns a tile of the level's output: lane l holds
+// the column pair (2j, 2j+1), j = j0 + l, for R + 2*halo rows, loaded straight from the four
+// subbands with coalesced 128-byte row reads (vh_synthesis interleave, :164-169).  Columns are
+// lifted with wavelet_index inside each thread (static register indices after unrolling); rows
+// are lifted with wavelet_index_ho by exchanging neighbours with warp shuffles (:172-175).  Halo
+// rows / lanes are recomputed by neighbouring tiles instead of being exchanged.  No shared
+// memory, no block-level barrier.  The edge clamps of lift1-4 (:210-212, :240-242) are
+// reproduced by refreshing out-of-range rows/lanes from the boundary sample of the same parity
+// before every stage -- only in tiles that touch an edge.  The last level applies the rounding
+// shift (:177-182, shift from wavelet_index_ho :198-201), crops (:282), clips (:327), offsets
+// (:301) and stores packed uint16 pairs.
 #include "lifting.cuh"
 
 namespace vc2b {
 
-constexpr int kIdwtThreads = 256;
+constexpr int kIdwtWarps = 4;  // warps per CTA (independent of each other)
 
 struct LevelArgs {
     // input LL band and the level's high-pass bands, per component
@@ -37,85 +43,237 @@ struct LevelArgs {
     int32_t ncomp;
 };
 
-template <int FV, int FH, bool VERT, int TW, int TH>
-__global__ void __launch_bounds__(kIdwtThreads)
+// ---- register-resident vertical lifting -----------------------------------------------------
+
+// One lifting stage down a column held in registers a[0..NR) (window row i = global row ys + i,
+// ys even).  Sources are clamped to the window: rows nearer than `halo` to a window edge that
+// is not a picture edge come out wrong and are never consumed.
+template <int TYPE, int S, int L, int D, int T0, int T1, int T2, int T3, int T4, int T5, int T6, int T7, int NR>
+__device__ __forceinline__ void vstage(int (&a)[NR])
+{
+    constexpr int taps[8] = {T0, T1, T2, T3, T4, T5, T6, T7};
+    constexpr bool kEven = (TYPE == 1 || TYPE == 2);
+    constexpr bool kAdd = (TYPE == 1 || TYPE == 3);
+#pragma unroll
+    for (int n = 0; n < NR / 2; n++) {
+        typename std::conditional<(S >= 8), long long, int>::type sum = 0;
+#pragma unroll
+        for (int i = D; i < L + D; i++) {
+            int pos = kEven ? 2 * (n + i) - 1 : 2 * (n + i);
+            pos = pos < 0 ? (kEven ? 1 : 0) : pos;
+            pos = pos > NR - 1 ? (kEven ? NR - 1 : NR - 2) : pos;
+            sum += (decltype(sum))taps[i - D] * a[pos];
+        }
+        if (S > 0) sum += (decltype(sum))1 << (S > 0 ? S - 1 : 0);
+        sum >>= S;
+        if (kAdd) a[kEven ? 2 * n : 2 * n + 1] += (int)sum;
+        else a[kEven ? 2 * n : 2 * n + 1] -= (int)sum;
+    }
+}
+
+// lift1-4 clamp their source positions to the array (picture_decoding.py:210-212, :240-242):
+// a source row outside the picture reads the nearest in-range row of the same parity, with the
+// value it has when the stage runs.  PAR = parity of the rows the coming stage READS.
+// top: window rows [0, kt) lie above the picture (kt = 0 unless the tile is on the top edge);
+// kb: first window row below the picture (>= NR when the tile does not reach the bottom).
+template <int PAR, int NR>
+__device__ __forceinline__ void vrefresh(int (&a)[NR], int kt, int kb)
+{
+    if (kt > 0) {
+        int bv = 0;
+#pragma unroll
+        for (int i = 0; i < NR; i++)
+            if ((i & 1) == PAR && i == kt + PAR) bv = a[i];
+#pragma unroll
+        for (int i = 0; i < NR; i++)
+            if ((i & 1) == PAR && i < kt) a[i] = bv;
+    }
+    if (kb < NR) {
+        int bv = 0;
+#pragma unroll
+        for (int i = 0; i < NR; i++)
+            if ((i & 1) == PAR && i == kb - 2 + PAR) bv = a[i];
+#pragma unroll
+        for (int i = 0; i < NR; i++)
+            if ((i & 1) == PAR && i >= kb) a[i] = bv;
+    }
+}
+
+template <int F, int SIDX, int NR>
+__device__ __forceinline__ void vrun_stage(int (&a)[NR], bool edge, int kt, int kb)
+{
+    constexpr FilterDef f = get_filter(F);
+    constexpr StageDef s = f.st[SIDX];
+    constexpr bool kEven = (s.type == 1 || s.type == 2);
+    if (edge) vrefresh<kEven ? 1 : 0, NR>(a, kt, kb);
+    vstage<s.type, s.S, s.L, s.D, s.taps[0], s.taps[1], s.taps[2], s.taps[3], s.taps[4], s.taps[5], s.taps[6],
+           s.taps[7], NR>(a);
+}
+
+template <int F, int NR>
+__device__ __forceinline__ void vlift(int (&a)[NR], bool edge, int kt, int kb)
+{
+    constexpr int ns = get_filter(F).nstages;
+    vrun_stage<F, 0, NR>(a, edge, kt, kb);
+    if constexpr (ns > 1) vrun_stage<F, (ns > 1 ? 1 : 0), NR>(a, edge, kt, kb);
+    if constexpr (ns > 2) vrun_stage<F, (ns > 2 ? 2 : 0), NR>(a, edge, kt, kb);
+    if constexpr (ns > 3) vrun_stage<F, (ns > 3 ? 3 : 0), NR>(a, edge, kt, kb);
+}
+
+// ---- horizontal lifting across lanes ---------------------------------------------------------
+
+// One stage on one row: lane l holds E = sample 2j, O = sample 2j+1 (j = j0 + l).
+template <int TYPE, int S, int L, int D, int T0, int T1, int T2, int T3, int T4, int T5, int T6, int T7>
+__device__ __forceinline__ void hstage(int &E, int &O, int lane, bool edge, int lane_lo, int lane_hi)
+{
+    constexpr int taps[8] = {T0, T1, T2, T3, T4, T5, T6, T7};
+    constexpr bool kEven = (TYPE == 1 || TYPE == 2);
+    constexpr bool kAdd = (TYPE == 1 || TYPE == 3);
+    int src = kEven ? O : E;
+    if (edge) {  // replicate the boundary column of the source parity into out-of-range lanes
+        const int lo = __shfl_sync(0xffffffffu, src, lane_lo & 31);
+        const int hi = __shfl_sync(0xffffffffu, src, lane_hi & 31);
+        if (lane < lane_lo) src = lo;
+        if (lane > lane_hi) src = hi;
+    }
+    typename std::conditional<(S >= 8), long long, int>::type sum = 0;
+#pragma unroll
+    for (int i = D; i < L + D; i++) {
+        // even update reads odd sample index n+i-1; odd update reads even sample index n+i
+        const int delta = kEven ? i - 1 : i;
+        const int v = (delta == 0) ? src : __shfl_sync(0xffffffffu, src, (lane + delta) & 31);
+        sum += (decltype(sum))taps[i - D] * v;
+    }
+    if (S > 0) sum += (decltype(sum))1 << (S > 0 ? S - 1 : 0);
+    sum >>= S;
+    if (kEven) { if (kAdd) E += (int)sum; else E -= (int)sum; }
+    else { if (kAdd) O += (int)sum; else O -= (int)sum; }
+}
+
+template <int F, int SIDX>
+__device__ __forceinline__ void hrun_stage(int &E, int &O, int lane, bool edge, int lane_lo, int lane_hi)
+{
+    constexpr FilterDef f = get_filter(F);
+    constexpr StageDef s = f.st[SIDX];
+    hstage<s.type, s.S, s.L, s.D, s.taps[0], s.taps[1], s.taps[2], s.taps[3], s.taps[4], s.taps[5], s.taps[6],
+           s.taps[7]>(E, O, lane, edge, lane_lo, lane_hi);
+}
+
+template <int F>
+__device__ __forceinline__ void hlift(int &E, int &O, int lane, bool edge, int lane_lo, int lane_hi)
+{
+    constexpr int ns = get_filter(F).nstages;
+    hrun_stage<F, 0>(E, O, lane, edge, lane_lo, lane_hi);
+    if constexpr (ns > 1) hrun_stage<F, (ns > 1 ? 1 : 0)>(E, O, lane, edge, lane_lo, lane_hi);
+    if constexpr (ns > 2) hrun_stage<F, (ns > 2 ? 2 : 0)>(E, O, lane, edge, lane_lo, lane_hi);
+    if constexpr (ns > 3) hrun_stage<F, (ns > 3 ? 3 : 0)>(E, O, lane, edge, lane_lo, lane_hi);
+}
+
+// ---- the level kernel -------------------------------------------------------------------------
+
+template <int FV, int FH, bool VERT>
+struct TileCfg {
+    static constexpr int HV = VERT ? get_filter(FV).halo : 0;  // halo rows above / below
+    static constexpr int HL = get_filter(FH).halo / 2;         // halo lanes left / right
+    static constexpr int R = VERT ? (HV >= 8 ? 16 : 32) : 16;  // output rows per warp tile
+    static constexpr int NR = R + 2 * HV;                      // rows held per thread
+    static constexpr int WOUT = 2 * (32 - 2 * HL);             // output columns per warp tile
+};
+
+template <int FV, int FH, bool VERT>
+__global__ void __launch_bounds__(kIdwtWarps * 32)
 idwt_level_kernel(LevelArgs A)
 {
-    constexpr int HX = get_filter(FH).halo;
-    constexpr int HY = VERT ? get_filter(FV).halo : 0;
-    constexpr int TS = TW + 2 * HX + 1;  // +1: odd stride keeps the row pass off one bank
-    extern __shared__ int32_t tile[];
+    using C = TileCfg<FV, FH, VERT>;
+    constexpr int HV = C::HV, HL = C::HL, R = C::R, NR = C::NR, WOUT = C::WOUT;
 
+    const int lane = threadIdx.x & 31;
     const int c = blockIdx.y;
     const int pic = blockIdx.z;
-    const int tx = blockIdx.x % A.tiles_x[c];
-    const int ty = blockIdx.x / A.tiles_x[c];
+    const int tile = blockIdx.x * kIdwtWarps + (threadIdx.x >> 5);
+    const int tx = tile % A.tiles_x[c];
+    const int ty = tile / A.tiles_x[c];
     if (ty >= A.tiles_y[c]) return;
 
     const int w = A.w[c], h = A.h[c];
     const int W2 = 2 * w, H2 = VERT ? 2 * h : h;
-    const int X0 = tx * TW, Y0 = ty * TH;
-    const int gx0 = max(0, X0 - HX), gx1 = min(W2, X0 + TW + HX);
-    const int gy0 = max(0, Y0 - HY), gy1 = min(H2, Y0 + TH + HY);
-    const int rw = gx1 - gx0, rh = gy1 - gy0;
+    const int X0 = tx * WOUT, Y0 = ty * R;
+    const int j = (X0 >> 1) - HL + lane;          // column pair owned by this lane
+    const int jc = min(max(j, 0), w - 1);
+    const int lane_lo = HL - (X0 >> 1);           // lane of column pair 0 (<= 0 away from the edge)
+    const int lane_hi = lane_lo + w - 1;          // lane of the last column pair
+    const bool hedge = (lane_lo > 0) || (lane_hi < 31);
 
-    // ---- stage the interleaved subbands ------------------------------------------------
     const int32_t *ll = A.ll[c] + (long long)pic * A.ll_pic_stride[c];
     const int32_t *b0 = A.hb[c][0] + (long long)pic * A.hb_pic_stride;
+
+    int e[NR], o[NR];  // columns 2j and 2j+1, window rows [0, NR) = global rows ys + i
+    const int ys = Y0 - HV;
     if (VERT) {
         const int32_t *b1 = A.hb[c][1] + (long long)pic * A.hb_pic_stride;
         const int32_t *b2 = A.hb[c][2] + (long long)pic * A.hb_pic_stride;
-        const int sw = rw >> 1, sh = rh >> 1, sx0 = gx0 >> 1, sy0 = gy0 >> 1;
-        for (int i = threadIdx.x; i < sw * sh; i += kIdwtThreads) {
-            const int sy = i / sw, sx = i - sy * sw;
-            const long long g = (long long)(sy0 + sy) * w + sx0 + sx;
-            int32_t *t = &tile[(2 * sy) * TS + 2 * sx];
-            t[0] = __ldg(ll + g);
-            t[1] = __ldg(b0 + g);
-            t[TS] = __ldg(b1 + g);
-            t[TS + 1] = __ldg(b2 + g);
+        const int sy0 = ys >> 1;  // ys even (may be negative)
+#pragma unroll
+        for (int i = 0; i < NR / 2; i++) {
+            const int sy = min(max(sy0 + i, 0), h - 1);
+            const long long g = (long long)sy * w + jc;
+            e[2 * i] = __ldg(ll + g);
+            o[2 * i] = __ldg(b0 + g);
+            e[2 * i + 1] = __ldg(b1 + g);
+            o[2 * i + 1] = __ldg(b2 + g);
         }
+        const int kt = ys < 0 ? -ys : 0;
+        const int kb = H2 - ys;
+        const bool vedge = (kt > 0) || (kb < NR);
+        vlift<FV, NR>(e, vedge, kt, kb);
+        vlift<FV, NR>(o, vedge, kt, kb);
     } else {
-        const int sw = rw >> 1, sx0 = gx0 >> 1;
-        for (int i = threadIdx.x; i < sw * rh; i += kIdwtThreads) {
-            const int sy = i / sw, sx = i - sy * sw;
-            const long long g = (long long)(gy0 + sy) * w + sx0 + sx;
-            int32_t *t = &tile[sy * TS + 2 * sx];
-            t[0] = __ldg(ll + g);
-            t[1] = __ldg(b0 + g);
+#pragma unroll
+        for (int i = 0; i < NR; i++) {
+            const int sy = min(Y0 + i, h - 1);
+            const long long g = (long long)sy * w + jc;
+            e[i] = __ldg(ll + g);
+            o[i] = __ldg(b0 + g);
         }
     }
-    __syncthreads();
 
-    // ---- synthesis: columns first, then rows (picture_decoding.py:172-175) ---------------
-    if (VERT) lift_tile<FV, true, false>(tile, TS, rw, rh, gy0, H2);
-    lift_tile<FH, false, false>(tile, TS, rw, rh, gx0, W2);
-
-    // ---- rounding shift and store (interior of the tile only) ----------------------------
-    const int ox1 = min(W2, X0 + TW), oy1 = min(H2, Y0 + TH);
-    const int ow = ox1 - X0, oh = oy1 - Y0;
+    // rows of the tile: horizontal lifting, rounding shift, store
     const int shift = A.shift;
     const int rnd = shift > 0 ? (1 << (shift - 1)) : 0;
+    const bool lane_ok = (lane >= HL) && (lane < 32 - HL) && (j >= 0) && (j < w);
     if (A.final_u16) {
-        // idwt_pad_removal :282, clip_picture :327, offset_picture :301
         const int cw = A.crop_w[c], ch = A.crop_h[c];
         const int half = 1 << (A.depth[c] - 1);
         uint16_t *dst = A.pic[c] + (long long)pic * A.pic_pic_stride;
-        for (int i = threadIdx.x; i < ow * oh; i += kIdwtThreads) {
-            const int y = i / ow, x = i - y * ow;
-            const int gx = X0 + x, gy = Y0 + y;
-            if (gx < cw && gy < ch) {
-                int v = (tile[(gy - gy0) * TS + (gx - gx0)] + rnd) >> shift;
-                v = min(max(v, -half), half - 1) + half;
-                dst[(long long)gy * cw + gx] = (uint16_t)v;
+#pragma unroll
+        for (int i = 0; i < R; i++) {
+            const int gy = Y0 + i;
+            int E = e[HV + i], O = o[HV + i];
+            hlift<FH>(E, O, lane, hedge, lane_lo, lane_hi);
+            if (lane_ok && gy < ch) {
+                int v0 = (E + rnd) >> shift, v1 = (O + rnd) >> shift;
+                v0 = min(max(v0, -half), half - 1) + half;
+                v1 = min(max(v1, -half), half - 1) + half;
+                const long long idx = (long long)gy * cw + 2 * j;
+                if (2 * j + 1 < cw && !(reinterpret_cast<uintptr_t>(dst + idx) & 3)) {
+                    *reinterpret_cast<uint32_t *>(dst + idx) = (uint32_t)v0 | ((uint32_t)v1 << 16);
+                } else {
+                    if (2 * j < cw) dst[idx] = (uint16_t)v0;
+                    if (2 * j + 1 < cw) dst[idx + 1] = (uint16_t)v1;
+                }
             }
         }
     } else {
         int32_t *dst = A.out[c] + (long long)pic * A.out_pic_stride[c];
-        for (int i = threadIdx.x; i < ow * oh; i += kIdwtThreads) {
-            const int y = i / ow, x = i - y * ow;
-            const int gx = X0 + x, gy = Y0 + y;
-            dst[(long long)gy * W2 + gx] = (tile[(gy - gy0) * TS + (gx - gx0)] + rnd) >> shift;
+#pragma unroll
+        for (int i = 0; i < R; i++) {
+            const int gy = Y0 + i;
+            int E = e[HV + i], O = o[HV + i];
+            hlift<FH>(E, O, lane, hedge, lane_lo, lane_hi);
+            if (lane_ok && gy < H2) {
+                int2 v = make_int2((E + rnd) >> shift, (O + rnd) >> shift);
+                *reinterpret_cast<int2 *>(dst + (long long)gy * W2 + 2 * j) = v;
+            }
         }
     }
 }
@@ -145,26 +303,16 @@ __global__ void idwt_copy_kernel(LevelArgs A)
 template <int FV, int FH, bool VERT>
 static int launch_level_t(const LevelArgs &A_in, int npic, cudaStream_t s)
 {
-    constexpr int HX = get_filter(FH).halo;
-    constexpr int HY = VERT ? get_filter(FV).halo : 0;
-    constexpr int TW = 128;
-    constexpr int TH = (HY >= 8) ? 64 : 32;
-    constexpr int TS = TW + 2 * HX + 1;
-    constexpr size_t smem = sizeof(int32_t) * (size_t)TS * (TH + 2 * HY);
+    using C = TileCfg<FV, FH, VERT>;
     LevelArgs A = A_in;
     int maxtiles = 0;
     for (int c = 0; c < A.ncomp; c++) {
-        A.tiles_x[c] = (2 * A.w[c] + TW - 1) / TW;
-        A.tiles_y[c] = ((VERT ? 2 : 1) * A.h[c] + TH - 1) / TH;
+        A.tiles_x[c] = (2 * A.w[c] + C::WOUT - 1) / C::WOUT;
+        A.tiles_y[c] = ((VERT ? 2 : 1) * A.h[c] + C::R - 1) / C::R;
         maxtiles = max(maxtiles, A.tiles_x[c] * A.tiles_y[c]);
     }
-    auto kern = idwt_level_kernel<FV, FH, VERT, TW, TH>;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-    }
-    dim3 grid(maxtiles, A.ncomp, npic);
-    kern<<<grid, kIdwtThreads, smem, s>>>(A);
+    dim3 grid((maxtiles + kIdwtWarps - 1) / kIdwtWarps, A.ncomp, npic);
+    idwt_level_kernel<FV, FH, VERT><<<grid, kIdwtWarps * 32, 0, s>>>(A);
     VC2B_CHECK_LAUNCH();
     return 0;
 }
@@ -225,8 +373,8 @@ static void plan_scratch(const DevParams &P, int c0, int c1, ScratchPlan *sp)
         }
         sp->comp_off_a[c] = sp->size_a;
         sp->comp_off_b[c] = sp->size_b;
-        sp->size_a += a;
-        sp->size_b += b;
+        sp->size_a += (a + 3) & ~3LL;  // keep every region 16-byte aligned (paired stores)
+        sp->size_b += (b + 3) & ~3LL;
     }
 }
 
@@ -317,7 +465,8 @@ int64_t vc2b_transform_scratch_bytes(const vc2b_params *p)
     ScratchPlan sp;
     plan_scratch(P, 0, 3, &sp);
     long long n = sp.size_a + sp.size_b;
-    return (n > 0 ? n : 1) * (long long)sizeof(int32_t);
+    // regions are 16-byte aligned so that paired stores stay aligned
+    return ((n > 0 ? n : 1) * (long long)sizeof(int32_t) + 15) & ~15LL;
 }
 
 int vc2b_idwt(const vc2b_params *p, const int32_t *d_coeffs, int npictures, uint16_t *d_pictures,
