@@ -19,6 +19,8 @@ LIB = os.path.join(OUT_DIR, "libvc2b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+if os.environ.get("VC2B_DEV_BUILD"):  # developer-only: a single filter pair, seconds to compile
+    FLAGS.append("-DVC2B_DEV_BUILD")
 
 
 def sources():

@@ -18,7 +18,7 @@
 // before every stage -- only in tiles that touch an edge.  The last level applies the rounding
 // shift (:177-182, shift from wavelet_index_ho :198-201), crops (:282), clips (:327), offsets
 // (:301) and stores packed uint16 pairs.
-#include "lifting.cuh"
+#include "stream_lift.cuh"
 
 namespace vc2b {
 
@@ -278,6 +278,187 @@ idwt_level_kernel(LevelArgs A)
     }
 }
 
+// ---- streaming 2-D level kernel ------------------------------------------------------------------
+//
+// One warp (one CTA) owns a strip: WOUT output columns wide, RSP row pairs tall.  It walks down
+// the strip one row pair per step: prefetch the raw pair P steps ahead (LL/HL -> even row,
+// LH/HH -> odd row), advance every vertical lifting stage by one pair (stream_lift.cuh), then
+// lift the finished pair's two rows horizontally across lanes, shift, clip, offset and store.
+// No vertical halo is recomputed inside a strip (only `warm` pairs at its top).
+
+template <int FV, int FH>
+struct StripCfg {
+    static constexpr StreamPlan P = make_stream_plan(FV);
+    static constexpr int RING = P.ring;
+    static constexpr int STEPS = 64;                           // steps per strip (multiple of RING)
+    static constexpr int RSP = STEPS - P.warm - P.maxlag;      // output row pairs per strip
+    static constexpr int HL = get_filter(FH).halo / 2;         // halo lanes left / right
+    static constexpr int WOUT = 2 * (32 - 2 * HL);
+};
+
+struct StripCtx {
+    const int32_t *ll, *b0, *b1, *b2;
+    int w, h, jc, j, lane, lane_lo, lane_hi;
+    bool lane_ok, hedge;
+    int shift, rnd;
+    // final output
+    uint16_t *pic;
+    int cw, ch, half;
+    int32_t *out;
+    int W2;
+};
+
+template <int RING>
+__device__ __forceinline__ void load_pair(const StripCtx &X, int m, int &ee, int &eo, int &oe, int &oo)
+{
+    const int sy = min(max(m, 0), X.h - 1);
+    const int idx = sy * X.w + X.jc;
+    ee = __ldg(X.ll + idx);
+    eo = __ldg(X.b0 + idx);
+    oe = __ldg(X.b1 + idx);
+    oo = __ldg(X.b2 + idx);
+}
+
+template <int FH, bool FINAL>
+__device__ __forceinline__ void finish_row(const StripCtx &X, int gy, int E, int O)
+{
+    hlift<FH>(E, O, X.lane, X.hedge, X.lane_lo, X.lane_hi);
+    if (FINAL) {
+        if (X.lane_ok && gy < X.ch) {
+            int v0 = (E + X.rnd) >> X.shift, v1 = (O + X.rnd) >> X.shift;
+            v0 = min(max(v0, -X.half), X.half - 1) + X.half;
+            v1 = min(max(v1, -X.half), X.half - 1) + X.half;
+            uint16_t *d = X.pic + (long long)gy * X.cw + 2 * X.j;
+            if (2 * X.j + 1 < X.cw && !(reinterpret_cast<uintptr_t>(d) & 3)) {
+                *reinterpret_cast<uint32_t *>(d) = (uint32_t)v0 | ((uint32_t)v1 << 16);
+            } else {
+                if (2 * X.j < X.cw) d[0] = (uint16_t)v0;
+                if (2 * X.j + 1 < X.cw) d[1] = (uint16_t)v1;
+            }
+        }
+    } else {
+        if (X.lane_ok) {
+            int2 v = make_int2((E + X.rnd) >> X.shift, (O + X.rnd) >> X.shift);
+            *reinterpret_cast<int2 *>(X.out + (long long)gy * X.W2 + 2 * X.j) = v;
+        }
+    }
+}
+
+template <int FV, int FH, bool FINAL, int U>
+__device__ __forceinline__ void strip_step_fast(PairRing<StripCfg<FV, FH>::RING> &R, const StripCtx &X, int t,
+                                                int K0, int K1)
+{
+    using C = StripCfg<FV, FH>;
+    constexpr int RING = C::RING, M = RING - 1;
+    constexpr int PF = C::P.prefetch;
+    load_pair<RING>(X, t + PF, R.v[0][0][(U + PF) & M], R.v[0][1][(U + PF) & M], R.v[1][0][(U + PF) & M],
+                    R.v[1][1][(U + PF) & M]);
+    vstep_fast<FV, U, RING, 2>(R);
+    const int kf = t - C::P.maxlag;
+    if (kf >= K0 && kf < K1) {
+        constexpr int sl = (U - C::P.maxlag) & M;
+        finish_row<FH, FINAL>(X, 2 * kf, R.v[0][0][sl], R.v[0][1][sl]);
+        finish_row<FH, FINAL>(X, 2 * kf + 1, R.v[1][0][sl], R.v[1][1][sl]);
+    }
+}
+
+template <int FV, int FH, bool FINAL, int U>
+__device__ __forceinline__ void strip_block_fast(PairRing<StripCfg<FV, FH>::RING> &R, const StripCtx &X, int t0,
+                                                 int K0, int K1)
+{
+    strip_step_fast<FV, FH, FINAL, U>(R, X, t0 + U, K0, K1);
+    if constexpr (U + 1 < StripCfg<FV, FH>::RING) strip_block_fast<FV, FH, FINAL, U + 1>(R, X, t0, K0, K1);
+}
+
+template <int FV, int FH, bool FINAL>
+__device__ __forceinline__ void strip_step_slow(PairRing<StripCfg<FV, FH>::RING> &R, const StripCtx &X, int t,
+                                                int ks, int last, int K0, int K1)
+{
+    using C = StripCfg<FV, FH>;
+    constexpr int RING = C::RING, M = RING - 1;
+    int ee, eo, oe, oo;
+    load_pair<RING>(X, t + C::P.prefetch, ee, eo, oe, oo);
+    const int ls = (t + C::P.prefetch - ks) & M;
+#pragma unroll
+    for (int i = 0; i < RING; i++)
+        if (i == ls) { R.v[0][0][i] = ee; R.v[0][1][i] = eo; R.v[1][0][i] = oe; R.v[1][1][i] = oo; }
+    vstep_slow<FV, RING, 2>(R, t, ks, last);
+    const int kf = t - C::P.maxlag;
+    if (kf >= K0 && kf < K1) {
+        const int sl = (kf - ks) & M;
+        finish_row<FH, FINAL>(X, 2 * kf, ring_get_dyn<RING>(R.v[0][0], sl), ring_get_dyn<RING>(R.v[0][1], sl));
+        finish_row<FH, FINAL>(X, 2 * kf + 1, ring_get_dyn<RING>(R.v[1][0], sl), ring_get_dyn<RING>(R.v[1][1], sl));
+    }
+}
+
+template <int FV, int FH, bool FINAL>
+__device__ __forceinline__ void run_strip(const StripCtx &X, int ty)
+{
+    using C = StripCfg<FV, FH>;
+    constexpr int RING = C::RING;
+    PairRing<RING> R;
+#pragma unroll
+    for (int i = 0; i < RING; i++) R.v[0][0][i] = R.v[0][1][i] = R.v[1][0][i] = R.v[1][1][i] = 0;
+    const int last = X.h - 1;
+    const int K0 = ty * C::RSP, K1 = min(K0 + C::RSP, X.h);
+    const int ks = K0 - C::P.warm;
+#pragma unroll
+    for (int u = 0; u < C::P.prefetch; u++)
+        load_pair<RING>(X, ks + u, R.v[0][0][u], R.v[0][1][u], R.v[1][0][u], R.v[1][1][u]);
+    const int t_end = K1 - 1 + C::P.maxlag;  // last step that finishes a pair of this strip
+    for (int t0 = ks; t0 <= t_end; t0 += RING) {
+        if (t0 >= C::P.back && t0 + RING - 1 <= last) {
+            strip_block_fast<FV, FH, FINAL, 0>(R, X, t0, K0, K1);
+        } else {
+#pragma unroll 1
+            for (int u = 0; u < RING; u++) strip_step_slow<FV, FH, FINAL>(R, X, t0 + u, ks, last, K0, K1);
+        }
+    }
+}
+
+template <int FV, int FH>
+__global__ void __launch_bounds__(32)
+idwt_stream_kernel(LevelArgs A)
+{
+    using C = StripCfg<FV, FH>;
+    const int c = blockIdx.y;
+    const int pic = blockIdx.z;
+    const int tx = blockIdx.x % A.tiles_x[c];
+    const int ty = blockIdx.x / A.tiles_x[c];
+    if (ty >= A.tiles_y[c]) return;
+
+    StripCtx X;
+    X.lane = threadIdx.x;
+    X.w = A.w[c];
+    X.h = A.h[c];
+    const int X0 = tx * C::WOUT;
+    X.j = (X0 >> 1) - C::HL + X.lane;
+    X.jc = min(max(X.j, 0), X.w - 1);
+    X.lane_lo = C::HL - (X0 >> 1);
+    X.lane_hi = X.lane_lo + X.w - 1;
+    X.lane_ok = (X.lane >= C::HL) && (X.lane < 32 - C::HL) && (X.j >= 0) && (X.j < X.w);
+    X.ll = A.ll[c] + (long long)pic * A.ll_pic_stride[c];
+    X.b0 = A.hb[c][0] + (long long)pic * A.hb_pic_stride;
+    X.b1 = A.hb[c][1] + (long long)pic * A.hb_pic_stride;
+    X.b2 = A.hb[c][2] + (long long)pic * A.hb_pic_stride;
+    X.shift = A.shift;
+    X.rnd = A.shift > 0 ? (1 << (A.shift - 1)) : 0;
+    X.pic = A.pic[c] + (long long)pic * A.pic_pic_stride;
+    X.cw = A.crop_w[c];
+    X.ch = A.crop_h[c];
+    X.half = 1 << (A.depth[c] - 1);
+    X.out = A.out[c] + (long long)pic * A.out_pic_stride[c];
+    X.W2 = 2 * X.w;
+    X.hedge = (X.lane_lo > 0) || (X.lane_hi < 31);
+    if (A.final_u16) run_strip<FV, FH, true>(X, ty); else run_strip<FV, FH, false>(X, ty);
+}
+
+}  // namespace vc2b
+
+#include "idwt8.cuh"
+
+namespace vc2b {
+
 // No transform at all (dwt_depth == dwt_depth_ho == 0): picture = level-0 band.
 __global__ void idwt_copy_kernel(LevelArgs A)
 {
@@ -303,16 +484,30 @@ __global__ void idwt_copy_kernel(LevelArgs A)
 template <int FV, int FH, bool VERT>
 static int launch_level_t(const LevelArgs &A_in, int npic, cudaStream_t s)
 {
-    using C = TileCfg<FV, FH, VERT>;
     LevelArgs A = A_in;
     int maxtiles = 0;
-    for (int c = 0; c < A.ncomp; c++) {
-        A.tiles_x[c] = (2 * A.w[c] + C::WOUT - 1) / C::WOUT;
-        A.tiles_y[c] = ((VERT ? 2 : 1) * A.h[c] + C::R - 1) / C::R;
-        maxtiles = max(maxtiles, A.tiles_x[c] * A.tiles_y[c]);
+    if constexpr (VERT && Strip8Cfg<FV, FH>::kSupported && (FV == FH || (FV == 5 && FH == 6))) {
+        if (level_is_wide_ok(A, npic)) return launch_wide<FV, FH>(A, npic, s);
     }
-    dim3 grid((maxtiles + kIdwtWarps - 1) / kIdwtWarps, A.ncomp, npic);
-    idwt_level_kernel<FV, FH, VERT><<<grid, kIdwtWarps * 32, 0, s>>>(A);
+    if constexpr (VERT) {
+        using C = StripCfg<FV, FH>;
+        for (int c = 0; c < A.ncomp; c++) {
+            A.tiles_x[c] = (2 * A.w[c] + C::WOUT - 1) / C::WOUT;
+            A.tiles_y[c] = (A.h[c] + C::RSP - 1) / C::RSP;
+            maxtiles = max(maxtiles, A.tiles_x[c] * A.tiles_y[c]);
+        }
+        dim3 grid(maxtiles, A.ncomp, npic);
+        idwt_stream_kernel<FV, FH><<<grid, 32, 0, s>>>(A);
+    } else {
+        using C = TileCfg<FV, FH, false>;
+        for (int c = 0; c < A.ncomp; c++) {
+            A.tiles_x[c] = (2 * A.w[c] + C::WOUT - 1) / C::WOUT;
+            A.tiles_y[c] = (A.h[c] + C::R - 1) / C::R;
+            maxtiles = max(maxtiles, A.tiles_x[c] * A.tiles_y[c]);
+        }
+        dim3 grid((maxtiles + kIdwtWarps - 1) / kIdwtWarps, A.ncomp, npic);
+        idwt_level_kernel<FV, FH, false><<<grid, kIdwtWarps * 32, 0, s>>>(A);
+    }
     VC2B_CHECK_LAUNCH();
     return 0;
 }
@@ -320,6 +515,9 @@ static int launch_level_t(const LevelArgs &A_in, int npic, cudaStream_t s)
 template <int FV, bool VERT>
 static int launch_level_h(int fh, const LevelArgs &A, int npic, cudaStream_t s)
 {
+#ifdef VC2B_DEV_BUILD
+    return VC2B_E_UNSUPPORTED;
+#else
     switch (fh) {
     case 0: return launch_level_t<FV, 0, VERT>(A, npic, s);
     case 1: return launch_level_t<FV, 1, VERT>(A, npic, s);
@@ -328,6 +526,7 @@ static int launch_level_h(int fh, const LevelArgs &A, int npic, cudaStream_t s)
     case 5: return launch_level_t<FV, 5, VERT>(A, npic, s);
     default: return launch_level_t<FV, 6, VERT>(A, npic, s);
     }
+#endif
 }
 
 static int launch_level(int fv, int fh, bool vert, const LevelArgs &A, int npic, cudaStream_t s)
@@ -335,6 +534,10 @@ static int launch_level(int fv, int fh, bool vert, const LevelArgs &A, int npic,
     // Haar with and without shift share their lifting stages (the shift is a runtime argument)
     if (fv == 4) fv = 3;
     if (fh == 4) fh = 3;
+#ifdef VC2B_DEV_BUILD  // quick developer builds: Deslauriers-Dubuc (9,7) only
+    if (fh != 0 || (vert && fv != 0)) return VC2B_E_UNSUPPORTED;
+    return vert ? launch_level_t<0, 0, true>(A, npic, s) : launch_level_t<0, 0, false>(A, npic, s);
+#endif
     if (!vert) return launch_level_h<0, false>(fh, A, npic, s);
     switch (fv) {
     case 0: return launch_level_h<0, true>(fh, A, npic, s);
