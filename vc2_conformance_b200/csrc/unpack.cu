@@ -31,8 +31,17 @@ constexpr int kErrOk = 0x7fffffff;
 // bytes of each slice (decoder/transform_data_syntax.py:216-244).
 // ---------------------------------------------------------------------------
 constexpr int kWalkChunk = 32768;
-constexpr int kWalkThreads = 256;
+constexpr int kWalkThreads = 1024;
 
+// Where slice n starts depends on the three length bytes of every earlier slice, so the walk is a
+// dependent chain (3 loads per slice).  It is broken by SPECULATION: all 1024 threads guess the
+// starts of the next 1024 slices -- from the closed form of a constant-bit-rate encoder
+// (make_transform_data_hq_lossy, encoder/pictures.py:617: slice n carries
+// scaler * (floor((n+1)T/N) - floor(nT/N)) coefficient bytes) or from a constant stride -- read the
+// length bytes at the guessed positions in parallel and keep the longest verified prefix (a guess is
+// confirmed when the previous slice, itself confirmed, ends exactly there).  Streams that defeat
+// both predictors fall back to the serial chase through shared-memory chunks.  The result is always
+// the true chain; speculation only changes the speed.
 __global__ void __launch_bounds__(kWalkThreads)
 hq_walk_kernel(DevParams P, const uint8_t *__restrict__ data, const int64_t *__restrict__ pic_offset,
                int npictures, uint32_t *__restrict__ slice_offset, int32_t *__restrict__ status)
@@ -41,8 +50,12 @@ hq_walk_kernel(DevParams P, const uint8_t *__restrict__ data, const int64_t *__r
     __shared__ long long s_pos;
     __shared__ int s_n;
     __shared__ int s_err;
+    __shared__ int s_first_bad;
+    __shared__ long long s_last_end, s_last_size;
+    __shared__ int s_eof_slice;
 
     const int pic = blockIdx.x;
+    const int tid = threadIdx.x;
     const long long pic_base = pic_offset[pic];
     const long long nbytes = pic_offset[pic + 1] - pic_base;
     const long long data_limit = (pic_offset[npictures] + 15) & ~15LL;  // caller pads >= 16 bytes
@@ -50,11 +63,82 @@ hq_walk_kernel(DevParams P, const uint8_t *__restrict__ data, const int64_t *__r
     const int nslices = P.slices_x * P.slices_y;
     const int scaler = P.slice_size_scaler;
     const int prefix = P.slice_prefix_bytes;
+    const int hdr = prefix + 4;
     uint32_t *so = slice_offset + (size_t)pic * nslices;
 
-    if (threadIdx.x == 0) { s_pos = 0; s_n = 0; s_err = kErrOk; }
+    if (tid == 0) { s_pos = 0; s_n = 0; s_err = kErrOk; }
     __syncthreads();
 
+    // ---- speculative phase --------------------------------------------------------------------
+    const long long T = nbytes - (long long)nslices * hdr;
+    const bool closed_ok = (T >= 0) && (T % scaler == 0);
+    const long long Tq = closed_ok ? T / scaler : 0;
+    int mode = closed_ok ? 0 : 1;   // 0: closed form, 1: constant stride
+    long long stride = 0;           // size of the last confirmed slice
+    int strikes = 0;
+    while (true) {
+        const int n0 = s_n;
+        const long long pos0 = s_pos;
+        if (n0 >= nslices || s_err != kErrOk || strikes >= 2) break;
+        __syncthreads();  // everybody has read s_n / s_pos
+        if (tid == 0) { s_first_bad = kWalkThreads; s_eof_slice = 0x7fffffff; }
+        __syncthreads();
+        const int m = n0 + tid;
+        long long guess, guess_next;
+        if (mode == 0) {
+            const long long shift = pos0 - ((long long)n0 * hdr + scaler * (((long long)n0 * Tq) / nslices));
+            guess = (long long)m * hdr + scaler * (((long long)m * Tq) / nslices) + shift;
+            guess_next = (long long)(m + 1) * hdr + scaler * (((long long)(m + 1) * Tq) / nslices) + shift;
+        } else {
+            guess = pos0 + (long long)tid * stride;
+            guess_next = guess + stride;
+        }
+        long long end = 0;
+        bool link_ok = false;
+        if (m < nslices) {
+            auto rd = [&](long long q) -> long long { return (q >= 0 && q < nbytes) ? (long long)__ldg(base + q) : 0; };
+            const long long p1 = guess + prefix + 2 + scaler * rd(guess + prefix + 1);
+            const long long p2 = p1 + 1 + scaler * rd(p1);
+            end = p2 + 1 + scaler * rd(p2);
+            // my start is confirmed iff every earlier link of this round holds; my own link holds
+            // when I end exactly where the next guess starts (the last slice has no successor)
+            link_ok = (end == guess_next) || (m == nslices - 1);
+            if (mode == 1 && stride == 0) link_ok = false;  // no stride learnt yet: only thread 0 is real
+            if (!link_ok) atomicMin(&s_first_bad, tid);
+        }
+        __syncthreads();
+        // slices n0 .. n0+fb have true starts and ends
+        const int fb = min(min(s_first_bad, kWalkThreads - 1), nslices - 1 - n0);
+        if (m < nslices && tid <= fb && end > nbytes) atomicMin(&s_eof_slice, m);  // decoder/io.py:197
+        __syncthreads();
+        const int eof = s_eof_slice;
+        if (m < nslices && tid <= fb && m < eof) so[m] = (uint32_t)guess;
+        if (eof != 0x7fffffff) {
+            if (m == eof) {
+                s_err = eof * 8 + VC2B_ST_UNEXPECTED_END_OF_STREAM;
+                s_n = eof;
+                s_pos = guess;
+            }
+            __syncthreads();
+            break;
+        }
+        if (tid == fb) { s_last_end = end; s_last_size = end - guess; }
+        __syncthreads();
+        const bool had_stride = !(mode == 1 && stride == 0);
+        stride = s_last_size;
+        const int confirmed = fb + 1;
+        if (tid == 0) { s_n = n0 + confirmed; s_pos = s_last_end; }
+        if (had_stride && confirmed < 16 && n0 + confirmed < nslices) {
+            strikes++;
+            mode = (mode == 0) ? 1 : (closed_ok ? 0 : 1);
+        } else if (had_stride) {
+            strikes = 0;
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+
+    // ---- serial fallback: chase through shared-memory chunks ---------------------------------------
     while (true) {
         long long pos = s_pos;
         int n = s_n;
@@ -62,14 +146,14 @@ hq_walk_kernel(DevParams P, const uint8_t *__restrict__ data, const int64_t *__r
         // chunk covers absolute bytes [a0, a0 + kWalkChunk), a0 16-byte aligned
         const long long abs0 = pic_base + pos;
         const long long a0 = abs0 & ~15LL;
-        for (int i = threadIdx.x; i < kWalkChunk / 16; i += kWalkThreads) {
+        for (int i = tid; i < kWalkChunk / 16; i += kWalkThreads) {
             long long a = a0 + 16LL * i;
             uint4 v = make_uint4(0, 0, 0, 0);
             if (a < data_limit) v = __ldg(reinterpret_cast<const uint4 *>(data + a));
             reinterpret_cast<uint4 *>(buf)[i] = v;
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
+        if (tid == 0) {
             const long long c0 = a0 - pic_base;  // chunk start in picture coordinates
             const long long c1 = c0 + kWalkChunk;
             auto rd = [&](long long q) -> int {
@@ -92,16 +176,17 @@ hq_walk_kernel(DevParams P, const uint8_t *__restrict__ data, const int64_t *__r
                 pos = nx;
                 if (pos + 1024 > c1) break;  // refill (slow global reads still correct otherwise)
             }
-            if (err != kErrOk) {
-                for (int k = n; k < nslices; k++) so[k] = 0xffffffffu;
-            }
             s_pos = pos;
             s_n = n;
             s_err = err;
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) {
+    // slices at or after a stream end are marked so that the unpack kernel skips them
+    if (s_err != kErrOk) {
+        for (int k = s_n + tid; k < nslices; k += kWalkThreads) so[k] = 0xffffffffu;
+    }
+    if (tid == 0) {
         status[4 * pic + 0] = s_err;
         status[4 * pic + 1] = 0;
         status[4 * pic + 2] = (int32_t)s_pos;
@@ -154,30 +239,54 @@ __global__ void finalize_status_kernel(int npictures, int32_t *__restrict__ stat
 // ---------------------------------------------------------------------------
 // warp-level bounded-block decoder
 // ---------------------------------------------------------------------------
+//
+// Round = 1024 bits of the block = one 32-bit word per lane.
+//  A. lane <-> word: a byte LUT gives, for each of the four entry states of the exp-Golomb state
+//     machine, the exit state and the bitmask of positions where a code STARTS; a warp scan of the
+//     32 transition maps fixes every lane's entry state, a prefix sum of the popcounts numbers
+//     the codes, and each lane lists the start positions of its codes in shared memory.
+//  B. lane <-> code: lane c takes code c, c+32, ...: it reads the code's bits from the words
+//     staged in shared memory, decodes magnitude and sign, dequantises and stores.  All lanes
+//     work (no per-word imbalance) and consecutive lanes write consecutive coefficients, so the
+//     scatter into the subband rectangles is coalesced per rectangle row.
 
-struct WarpBands {        // per-warp table in shared memory, rebuilt per slice component
+constexpr int kMapMax = 512;        // coefficients of a slice component with a cached destination map
+constexpr int kRoundWords = 32;
+
+struct WarpBands {        // per-warp tables in shared memory, rebuilt per slice component
     int32_t cum[kMaxBands + 1];   // first coefficient index of each band in the slice
     int32_t w[kMaxBands];         // rectangle width
+    int32_t h[kMaxBands];         // rectangle height
     int32_t stride[kMaxBands];    // subband row stride
     int32_t base[kMaxBands];      // offset of the rectangle's first coefficient in the component
-    uint64_t qf[kMaxBands];       // quant_factor(quantizer)
-    uint64_t qo[kMaxBands];       // quant_offset(quantizer) + 2
+    uint32_t qf[kMaxBands];       // quant_factor(quantizer), saturated to 2^32-1
+    uint32_t qo[kMaxBands];       // quant_offset(quantizer) + 2
+    int32_t map_w[2][kMaxBands];  // rectangle dims the cached maps (0 luma, 1 chroma) were built for
+    int32_t map_h[2][kMaxBands];
+    int32_t map_valid[2];
+};
+
+struct WarpScratch {
+    uint32_t words[kRoundWords + 4];     // the round's words (+ look-ahead for codes that run on)
+    uint16_t pos[kRoundWords * 32];      // start bit (within the round) of every code of the round
+    uint32_t map[2][kMapMax];            // [luma, chroma]: coefficient index -> band << 26 | y * stride + x
 };
 
 // State machine over the bit string.  0: at a code start, 1: next bit is a data bit,
 // 2: next bit is a follow bit and the code already has >= 1 data bit, 3: next bit is the sign.
-__device__ __forceinline__ void build_lut(uint8_t *lut, int tid, int nthreads)
+// LUT entry: exit state | start mask << 8 (bit 7 = first bit of the byte).
+__device__ __forceinline__ void build_lut(uint16_t *lut, int tid, int nthreads)
 {
     for (int e = tid; e < 1024; e += nthreads) {
-        int s = e >> 8, byte = e & 255, cnt = 0;
+        int s = e >> 8, byte = e & 255, mask = 0;
         for (int i = 7; i >= 0; i--) {
             int bit = (byte >> i) & 1;
-            if (s == 0) { cnt++; s = bit ? 0 : 1; }
+            if (s == 0) { mask |= 1 << i; s = bit ? 0 : 1; }
             else if (s == 1) s = 2;
             else if (s == 2) s = bit ? 3 : 1;
             else s = 0;
         }
-        lut[e] = (uint8_t)(s | (cnt << 2));
+        lut[e] = (uint16_t)(s | (mask << 8));
     }
 }
 
@@ -209,6 +318,17 @@ __device__ __forceinline__ uint32_t compose_maps(uint32_t a, uint32_t b)
     return r;
 }
 
+// destination of coefficient jj of the slice component: band and offset from the rectangle origin
+__device__ __forceinline__ uint32_t locate(const WarpBands &T, int nb, int jj)
+{
+    int b = 0;
+    while (b < nb - 1 && jj >= T.cum[b + 1]) b++;
+    const int local = jj - T.cum[b];
+    const int y = local / T.w[b];
+    const int x = local - y * T.w[b];
+    return ((uint32_t)b << 26) | (uint32_t)(y * T.stride[b] + x);
+}
+
 // Decodes `ncoef` values of the bounded block [start_bit, start_bit+nbits) of `base` and
 // scatters the dequantised coefficients.  INTERLEAVED: values alternate C1, C2
 // (color_diff_slice_band, decoder/transform_data_syntax.py:315); `out2` is then the C2 base.
@@ -216,35 +336,35 @@ __device__ __forceinline__ uint32_t compose_maps(uint32_t a, uint32_t b)
 // int32 envelope.
 template <bool INTERLEAVED>
 __device__ int decode_block(const uint8_t *__restrict__ base, long long start_bit, long long nbits,
-                            int ncoef, const WarpBands &T, int nb, int32_t *__restrict__ out,
-                            int32_t *__restrict__ out2, const uint8_t *__restrict__ lut, int lane)
+                            int ncoef, const WarpBands &T, WarpScratch &W, const uint32_t *__restrict__ cmap, int nb,
+                            int32_t *__restrict__ out, int32_t *__restrict__ out2,
+                            const uint16_t *__restrict__ lut, int lane)
 {
     int state_in = 0;
     int produced = 0;
     int maxabs = 0;
     bool overflow = false;
 
-    for (long long rbit = 0; produced < ncoef && rbit < nbits; rbit += 1024) {
-        const long long mybit = rbit + 32 * lane;
-        const uint32_t w0 = fetch_word(base, start_bit, mybit, nbits);
-        const uint32_t w1 = fetch_word(base, start_bit, mybit + 32, nbits);
-        const uint32_t w2 = fetch_word(base, start_bit, mybit + 64, nbits);
-
-        // transition map and code-start counts of this word for the four entry states
-        uint32_t map = 0, cnts = 0;
+    for (long long rbit = 0; produced < ncoef && rbit < nbits; rbit += 32 * kRoundWords) {
+        // ---- A: stage the round's words, find every code start ------------------------------
+        const uint32_t w0 = fetch_word(base, start_bit, rbit + 32 * lane, nbits);
+        __syncwarp();
+        W.words[lane] = w0;
+        if (lane < 3) W.words[kRoundWords + lane] = fetch_word(base, start_bit, rbit + 32 * (kRoundWords + lane), nbits);
+        uint32_t map = 0, mask_sel[4];
 #pragma unroll
         for (int s0 = 0; s0 < 4; s0++) {
-            int s = s0, c = 0;
+            int s = s0;
+            uint32_t m = 0;
 #pragma unroll
             for (int b = 3; b >= 0; b--) {
-                uint32_t e = lut[(s << 8) | ((w0 >> (8 * b)) & 255)];
+                const uint32_t e = lut[(s << 8) | ((w0 >> (8 * b)) & 255)];
                 s = e & 3;
-                c += e >> 2;
+                m |= (e >> 8) << (8 * b);
             }
             map |= s << (2 * s0);
-            cnts |= c << (8 * s0);
+            mask_sel[s0] = m;
         }
-        // inclusive scan of the maps
         uint32_t inc = map;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -254,7 +374,11 @@ __device__ int decode_block(const uint8_t *__restrict__ base, long long start_bi
         uint32_t exc = __shfl_up_sync(0xffffffffu, inc, 1);
         if (lane == 0) exc = 0xE4;  // identity
         const int s_start = (exc >> (2 * state_in)) & 3;
-        const int mycnt = (cnts >> (8 * s_start)) & 255;
+        uint32_t mask = mask_sel[0];
+        if (s_start == 1) mask = mask_sel[1];
+        if (s_start == 2) mask = mask_sel[2];
+        if (s_start == 3) mask = mask_sel[3];
+        const int mycnt = __popc(mask);
         int pre = mycnt;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -263,98 +387,84 @@ __device__ int decode_block(const uint8_t *__restrict__ base, long long start_bi
         }
         const int total = __shfl_sync(0xffffffffu, pre, 31);
         const int last_map = __shfl_sync(0xffffffffu, inc, 31);
-        int idx = produced + pre - mycnt;
         state_in = (last_map >> (2 * state_in)) & 3;
-        produced += total;
-
-        // first code start inside this word
-        int p;
-        if (s_start == 0) p = 0;
-        else if (s_start == 3) p = 1;
-        else {
-            uint32_t t = w0 & (0xAAAAAAAAu >> (s_start == 1 ? 1 : 0));
-            p = t ? __clz(t) + 2 : 32;
-        }
-
-        // destination cursor for coefficient `idx`
-        int jj = INTERLEAVED ? (idx >> 1) : idx;
-        int b = 0, x = 0, y = 0, bw = 1, next_cum = 0;
-        if (p < 32 && idx < ncoef) {
-            while (b < nb - 1 && jj >= T.cum[b + 1]) b++;
-            bw = T.w[b];
-            int local = jj - T.cum[b];
-            y = local / bw;
-            x = local - y * bw;
-            next_cum = T.cum[b + 1];
-        }
-
-        while (p < 32 && idx < ncoef) {
-            const uint32_t hi = __funnelshift_l(w1, w0, p);
-            const uint32_t lo = __funnelshift_l(w2, w1, p);
-            const unsigned long long win = ((unsigned long long)hi << 32) | lo;
-            const unsigned long long f = win & 0xAAAAAAAAAAAAAAAAull;
-            int32_t value = 0;
-            int len = 1;
-            if (f == 0) {  // 32 or more data bits: outside the int32 envelope
-                overflow = true;
-                break;
+        {
+            int c = pre - mycnt;
+            uint32_t m = mask;
+            while (m) {
+                const int bitpos = __clz(m);  // bit 31 = first bit of the word
+                W.pos[c++] = (uint16_t)(32 * lane + bitpos);
+                m &= ~(0x80000000u >> bitpos);
             }
-            const int k = __clzll((long long)f) >> 1;
-            if (k != 0) {
-                uint32_t d;
-                if (k <= 8) {
-                    uint32_t v = (uint32_t)(win >> (64 - 2 * k));
-                    v = (v | (v >> 1)) & 0x3333u;
-                    v = (v | (v >> 2)) & 0x0f0fu;
-                    v = (v | (v >> 4)) & 0x00ffu;
-                    d = v;
+        }
+        __syncwarp();
+
+        // ---- B: one code per lane ----------------------------------------------------------------
+        const int ncodes = min(total, ncoef - produced);
+        for (int c = lane; c < ncodes; c += 32) {
+            const int p = W.pos[c];
+            const int wi = p >> 5, sh = p & 31;
+            const uint32_t a0 = W.words[wi], a1 = W.words[wi + 1];
+            const uint32_t hi = __funnelshift_l(a1, a0, sh);
+            int32_t value = 0;
+            int k;
+            uint32_t mag = 0;
+            int neg = 0;
+            const uint32_t f = hi & 0xAAAAAAAAu;
+            if (f != 0) {  // at most 15 data bits: the whole code sits in 32 bits
+                k = __clz(f) >> 1;
+                if (k != 0) {
+                    uint32_t v = hi >> (32 - 2 * k);
+                    v = (v | (v >> 1)) & 0x33333333u;
+                    v = (v | (v >> 2)) & 0x0f0f0f0fu;
+                    v = (v | (v >> 4)) & 0x00ff00ffu;
+                    v = (v | (v >> 8)) & 0x0000ffffu;
+                    mag = ((1u << k) | v) - 1u;
+                    neg = (hi >> (30 - 2 * k)) & 1;
+                }
+            } else {
+                const uint32_t a2 = W.words[wi + 2];
+                const uint32_t lo = __funnelshift_l(a2, a1, sh);
+                const unsigned long long win = ((unsigned long long)hi << 32) | lo;
+                const unsigned long long ff = win & 0xAAAAAAAAAAAAAAAAull;
+                if (ff == 0) {  // 32 or more data bits: outside the int32 envelope
+                    overflow = true;
+                    k = 0;
                 } else {
+                    k = __clzll((long long)ff) >> 1;
                     unsigned long long v = win >> (64 - 2 * k);
                     v = (v | (v >> 1)) & 0x3333333333333333ull;
                     v = (v | (v >> 2)) & 0x0f0f0f0f0f0f0f0full;
                     v = (v | (v >> 4)) & 0x00ff00ff00ff00ffull;
                     v = (v | (v >> 8)) & 0x0000ffff0000ffffull;
                     v = (v | (v >> 16)) & 0x00000000ffffffffull;
-                    d = (uint32_t)v;
+                    mag = ((1u << k) | (uint32_t)v) - 1u;
+                    neg = (int)((win >> (62 - 2 * k)) & 1);
                 }
-                const uint32_t mag = ((1u << k) | d) - 1u;
-                const int neg = (int)((win >> (62 - 2 * k)) & 1);
+            }
+            const int idx = produced + c;
+            const int jj = INTERLEAVED ? (idx >> 1) : idx;
+            const uint32_t loc = cmap ? cmap[jj] : locate(T, nb, jj);
+            const int b = loc >> 26;
+            if (mag != 0) {
                 // inverse_quant (pseudocode/quantization.py:18): (m*qf + qo + 2) // 4
                 const unsigned long long t = ((unsigned long long)mag * T.qf[b] + T.qo[b]) >> 2;
-                if (t > 0x7fffffffull) overflow = true;
+                if (t > 0x7fffffffull || T.qf[b] == 0xffffffffu) overflow = true;
                 value = neg ? -(int32_t)t : (int32_t)t;
                 maxabs = max(maxabs, (int)t);
-                len = 2 * k + 2;
             }
             int32_t *dst = (INTERLEAVED && (idx & 1)) ? out2 : out;
-            dst[T.base[b] + y * T.stride[b] + x] = value;
-            p += len;
-            idx++;
-            if (!INTERLEAVED || !(idx & 1)) {
-                jj++;
-                x++;
-                if (x == bw) { x = 0; y++; }
-                if (jj == next_cum && idx < ncoef) {
-                    do { b++; } while (b < nb - 1 && jj >= T.cum[b + 1]);
-                    bw = T.w[b];
-                    next_cum = T.cum[b + 1];
-                    x = 0;
-                    y = 0;
-                }
-            }
+            dst[T.base[b] + (loc & 0x3ffffffu)] = value;
         }
+        produced += total;
     }
     if (produced > ncoef) produced = ncoef;
     // everything not reached before the block ran out is zero (code "1" from the 1-extension)
     for (int idx = produced + lane; idx < ncoef; idx += 32) {
-        int jj = INTERLEAVED ? (idx >> 1) : idx;
-        int b = 0;
-        while (b < nb - 1 && jj >= T.cum[b + 1]) b++;
-        int local = jj - T.cum[b];
-        int y = local / T.w[b];
-        int x = local - y * T.w[b];
+        const int jj = INTERLEAVED ? (idx >> 1) : idx;
+        const uint32_t loc = cmap ? cmap[jj] : locate(T, nb, jj);
         int32_t *dst = (INTERLEAVED && (idx & 1)) ? out2 : out;
-        dst[T.base[b] + y * T.stride[b] + x] = 0;
+        dst[T.base[loc >> 26] + (loc & 0x3ffffffu)] = 0;
     }
     overflow = __any_sync(0xffffffffu, overflow);
 #pragma unroll
@@ -364,12 +474,16 @@ __device__ int decode_block(const uint8_t *__restrict__ base, long long start_bi
 
 // slice rectangle + quantiser table for component `comp` of slice (sx, sy)
 // (slice_left/right/top/bottom pseudocode/slice_sizes.py:108-127, slice_quantizers
-// decoder/transform_data_syntax.py:255).  Returns the number of coefficients.
+// decoder/transform_data_syntax.py:255), and the coefficient -> destination map (reused from
+// the previous slice of this warp when the rectangles have the same dimensions).
+// Returns the number of coefficients; *use_map tells whether W.map is valid for it.
 __device__ __forceinline__ int build_bands(const DevParams &P, int comp, int sx, int sy, int qindex,
-                                           WarpBands &T, int lane)
+                                           WarpBands &T, WarpScratch &W, int map_id, bool *use_map, int lane)
 {
     const int nb = P.nb;
     int cnt = 0;
+    bool same = true;
+    __syncwarp();
     if (lane < nb) {
         const Band &B = P.band[comp][lane];
         int x1 = (int)(((long long)B.w * sx) / P.slices_x);
@@ -378,11 +492,16 @@ __device__ __forceinline__ int build_bands(const DevParams &P, int comp, int sx,
         int y2 = (int)(((long long)B.h * (sy + 1)) / P.slices_y);
         int q = max(qindex - B.qm, 0);
         T.w[lane] = max(x2 - x1, 1);
+        T.h[lane] = y2 - y1;
         T.stride[lane] = B.w;
         T.base[lane] = B.off + y1 * B.w + x1;
-        T.qf[lane] = quant_factor_u64(q);
-        T.qo[lane] = quant_offset_u64(q) + 2;
+        const uint64_t qf = quant_factor_u64(q);
+        T.qf[lane] = qf > 0xfffffffeull ? 0xffffffffu : (uint32_t)qf;
+        T.qo[lane] = qf > 0xfffffffeull ? 0u : (uint32_t)quant_offset_u64(q) + 2u;
         cnt = (x2 - x1) * (y2 - y1);
+        same = T.map_valid[map_id] && (T.map_w[map_id][lane] == x2 - x1) && (T.map_h[map_id][lane] == y2 - y1);
+        T.map_w[map_id][lane] = x2 - x1;
+        T.map_h[map_id][lane] = y2 - y1;
     }
     int pre = cnt;
 #pragma unroll
@@ -392,8 +511,19 @@ __device__ __forceinline__ int build_bands(const DevParams &P, int comp, int sx,
     }
     if (lane < nb) T.cum[lane + 1] = pre;
     if (lane == 0) T.cum[0] = 0;
+    const int ncoef = __shfl_sync(0xffffffffu, pre, 31);
+    same = __all_sync(0xffffffffu, same);
     __syncwarp();
-    return __shfl_sync(0xffffffffu, pre, 31);
+    *use_map = ncoef <= kMapMax;
+    if (*use_map && !same) {
+        // the map stores band << 26 | (y * stride + x): stride is a property of the band, so the map
+        // only depends on the rectangle dimensions
+        for (int j = lane; j < ncoef; j += 32) W.map[map_id][j] = locate(T, nb, j);
+        if (lane == 0) T.map_valid[map_id] = 1;
+    }
+    if (!*use_map && lane == 0) T.map_valid[map_id] = 0;
+    __syncwarp();
+    return ncoef;
 }
 
 __device__ __forceinline__ void report(int32_t *status, int pic, int slice, int code)
@@ -407,43 +537,51 @@ unpack_hq_kernel(DevParams P, const uint8_t *__restrict__ data, const int64_t *_
                  int npictures, const uint32_t *__restrict__ slice_offset, int32_t *__restrict__ coeffs,
                  int32_t *__restrict__ qindex_out, int32_t *__restrict__ status)
 {
-    __shared__ uint8_t lut[1024];
+    __shared__ uint16_t lut[1024];
     __shared__ WarpBands tabs[kWarpsPerBlock];
+    __shared__ WarpScratch scratch[kWarpsPerBlock];
     build_lut(lut, threadIdx.x, blockDim.x);
+    if ((threadIdx.x & 31) == 0) tabs[threadIdx.x >> 5].map_valid[0] = tabs[threadIdx.x >> 5].map_valid[1] = 0;
     __syncthreads();
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int nslices = P.slices_x * P.slices_y;
-    const long long gw = (long long)blockIdx.x * kWarpsPerBlock + warp;
-    if (gw >= (long long)npictures * nslices) return;
-    const int pic = (int)(gw / nslices);
-    const int n = (int)(gw - (long long)pic * nslices);
-    const int sy = n / P.slices_x, sx = n - sy * P.slices_x;
-    const uint32_t off = slice_offset[gw];
-    if (off == 0xffffffffu) return;  // at or after the slice where the stream ended
-    const uint8_t *base = data + pic_offset[pic];
+    const long long total_slices = (long long)npictures * nslices;
     WarpBands &T = tabs[warp];
-    int32_t *pc = coeffs + (size_t)pic * P.pic_coeffs;
+    WarpScratch &W = scratch[warp];
+    // persistent warps: consecutive slices of a picture mostly share their rectangle dimensions,
+    // so the destination map survives from one slice to the next
+    const long long per_warp = (total_slices + (long long)gridDim.x * kWarpsPerBlock - 1) /
+                               ((long long)gridDim.x * kWarpsPerBlock);
+    const long long gw0 = ((long long)blockIdx.x * kWarpsPerBlock + warp) * per_warp;
+    for (long long gw = gw0; gw < gw0 + per_warp && gw < total_slices; gw++) {
+        const int pic = (int)(gw / nslices);
+        const int n = (int)(gw - (long long)pic * nslices);
+        const int sy = n / P.slices_x, sx = n - sy * P.slices_x;
+        const uint32_t off = slice_offset[gw];
+        if (off == 0xffffffffu) continue;  // at or after the slice where the stream ended
+        const uint8_t *base = data + pic_offset[pic];
+        int32_t *pc = coeffs + (size_t)pic * P.pic_coeffs;
 
-    long long pos = (long long)off + P.slice_prefix_bytes;
-    const int qindex = base[pos];
-    pos += 1;
-    if (qindex_out && lane == 0) qindex_out[gw] = qindex;
-    int maxabs = 0;
-    bool bad = false;
-    for (int c = 0; c < 3; c++) {
-        const long long length = (long long)P.slice_size_scaler * base[pos];
+        long long pos = (long long)off + P.slice_prefix_bytes;
+        const int qindex = base[pos];
         pos += 1;
-        __syncwarp();
-        const int ncoef = build_bands(P, c, sx, sy, qindex, T, lane);
-        int m = decode_block<false>(base, pos * 8, 8 * length, ncoef, T, P.nb, pc + P.comp_off[c], nullptr,
-                                    lut, lane);
-        if (m < 0) bad = true; else maxabs = max(maxabs, m);
-        pos += length;
-    }
-    if (lane == 0) {
-        atomicMax(&status[4 * pic + 3], bad ? 0x7fffffff : maxabs);
+        if (qindex_out && lane == 0) qindex_out[gw] = qindex;
+        int maxabs = 0;
+        bool bad = false;
+        for (int c = 0; c < 3; c++) {
+            const long long length = (long long)P.slice_size_scaler * base[pos];
+            pos += 1;
+            bool use_map;
+            // luma and chroma rectangles differ: the map is tagged with the component class
+            const int ncoef = build_bands(P, c, sx, sy, qindex, T, W, c == 0 ? 0 : 1, &use_map, lane);
+            int m = decode_block<false>(base, pos * 8, 8 * length, ncoef, T, W, use_map ? W.map[c == 0 ? 0 : 1] : nullptr,
+                                        P.nb, pc + P.comp_off[c], nullptr, lut, lane);
+            if (m < 0) bad = true; else maxabs = max(maxabs, m);
+            pos += length;
+        }
+        if (lane == 0) atomicMax(&status[4 * pic + 3], bad ? 0x7fffffff : maxabs);
     }
 }
 
@@ -453,55 +591,60 @@ unpack_ld_kernel(DevParams P, const uint8_t *__restrict__ data, const int64_t *_
                  int npictures, int32_t *__restrict__ coeffs, int32_t *__restrict__ qindex_out,
                  int32_t *__restrict__ status)
 {
-    __shared__ uint8_t lut[1024];
+    __shared__ uint16_t lut[1024];
     __shared__ WarpBands tabs[kWarpsPerBlock];
+    __shared__ WarpScratch scratch[kWarpsPerBlock];
     build_lut(lut, threadIdx.x, blockDim.x);
+    if ((threadIdx.x & 31) == 0) tabs[threadIdx.x >> 5].map_valid[0] = tabs[threadIdx.x >> 5].map_valid[1] = 0;
     __syncthreads();
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int nslices = P.slices_x * P.slices_y;
-    const long long gw = (long long)blockIdx.x * kWarpsPerBlock + warp;
-    if (gw >= (long long)npictures * nslices) return;
-    const int pic = (int)(gw / nslices);
-    const int n = (int)(gw - (long long)pic * nslices);
-    const int sy = n / P.slices_x, sx = n - sy * P.slices_x;
-    const long long nbytes = pic_offset[pic + 1] - pic_offset[pic];
-    const uint8_t *base = data + pic_offset[pic];
-    const long long s0 = ld_slice_offset(P, n), s1 = ld_slice_offset(P, n + 1);
-    if (s1 > nbytes) return;  // stream ended inside this slice (reported by ld_init_status_kernel)
-    const long long sbytes = s1 - s0;
+    const long long total_slices = (long long)npictures * nslices;
     WarpBands &T = tabs[warp];
-    int32_t *pc = coeffs + (size_t)pic * P.pic_coeffs;
+    WarpScratch &W = scratch[warp];
+    const long long per_warp = (total_slices + (long long)gridDim.x * kWarpsPerBlock - 1) /
+                               ((long long)gridDim.x * kWarpsPerBlock);
+    const long long gw0 = ((long long)blockIdx.x * kWarpsPerBlock + warp) * per_warp;
+    for (long long gw = gw0; gw < gw0 + per_warp && gw < total_slices; gw++) {
+        const int pic = (int)(gw / nslices);
+        const int n = (int)(gw - (long long)pic * nslices);
+        const int sy = n / P.slices_x, sx = n - sy * P.slices_x;
+        const long long nbytes = pic_offset[pic + 1] - pic_offset[pic];
+        const uint8_t *base = data + pic_offset[pic];
+        const long long s0 = ld_slice_offset(P, n), s1 = ld_slice_offset(P, n + 1);
+        if (s1 > nbytes) continue;  // stream ended inside this slice (reported by ld_init_status_kernel)
+        const long long sbytes = s1 - s0;
+        int32_t *pc = coeffs + (size_t)pic * P.pic_coeffs;
 
-    // 7-bit qindex, then intlog2(8*slice_bytes-7)-bit slice_y_length (read_nbits, decoder/io.py:230)
-    const int length_bits = ilog2_ceil(8 * sbytes - 7);
-    long long hdr = 0;  // up to 7 + 32 header bits, read bytewise
-    const int hbytes = (7 + length_bits + 7) >> 3;
-    for (int i = 0; i < hbytes; i++) hdr = (hdr << 8) | base[s0 + i];
-    hdr >>= (8 * hbytes - 7 - length_bits);
-    const int qindex = (int)(hdr >> length_bits);
-    const long long slice_y_length = hdr & ((1LL << length_bits) - 1);
-    long long bits_left = 8 * sbytes - 7 - length_bits;
-    if (qindex_out && lane == 0) qindex_out[gw] = qindex;
-    if (slice_y_length > bits_left) {  // InvalidSliceYLength, transform_data_syntax.py:166
-        if (lane == 0) report(status, pic, n, VC2B_ST_INVALID_SLICE_Y_LENGTH);
-        return;
-    }
-    const long long ybit = s0 * 8 + 7 + length_bits;
-    int maxabs = 0;
-    bool bad = false;
-    int ncoef = build_bands(P, 0, sx, sy, qindex, T, lane);
-    int m = decode_block<false>(base, ybit, slice_y_length, ncoef, T, P.nb, pc + P.comp_off[0], nullptr, lut,
-                                lane);
-    if (m < 0) bad = true; else maxabs = max(maxabs, m);
-    __syncwarp();
-    ncoef = build_bands(P, 1, sx, sy, qindex, T, lane);
-    m = decode_block<true>(base, ybit + slice_y_length, bits_left - slice_y_length, 2 * ncoef, T, P.nb,
-                           pc + P.comp_off[1], pc + P.comp_off[2], lut, lane);
-    if (m < 0) bad = true; else maxabs = max(maxabs, m);
-    if (lane == 0) {
-        atomicMax(&status[4 * pic + 3], bad ? 0x7fffffff : maxabs);
+        // 7-bit qindex, then intlog2(8*slice_bytes-7)-bit slice_y_length (read_nbits, decoder/io.py:230)
+        const int length_bits = ilog2_ceil(8 * sbytes - 7);
+        long long hdr = 0;  // up to 7 + 32 header bits, read bytewise
+        const int hbytes = (7 + length_bits + 7) >> 3;
+        for (int i = 0; i < hbytes; i++) hdr = (hdr << 8) | base[s0 + i];
+        hdr >>= (8 * hbytes - 7 - length_bits);
+        const int qindex = (int)(hdr >> length_bits);
+        const long long slice_y_length = hdr & ((1LL << length_bits) - 1);
+        long long bits_left = 8 * sbytes - 7 - length_bits;
+        if (qindex_out && lane == 0) qindex_out[gw] = qindex;
+        if (slice_y_length > bits_left) {  // InvalidSliceYLength, transform_data_syntax.py:166
+            if (lane == 0) report(status, pic, n, VC2B_ST_INVALID_SLICE_Y_LENGTH);
+            continue;
+        }
+        const long long ybit = s0 * 8 + 7 + length_bits;
+        int maxabs = 0;
+        bool bad = false;
+        bool use_map;
+        int ncoef = build_bands(P, 0, sx, sy, qindex, T, W, 0, &use_map, lane);
+        int m = decode_block<false>(base, ybit, slice_y_length, ncoef, T, W, use_map ? W.map[0] : nullptr, P.nb,
+                                    pc + P.comp_off[0], nullptr, lut, lane);
+        if (m < 0) bad = true; else maxabs = max(maxabs, m);
+        ncoef = build_bands(P, 1, sx, sy, qindex, T, W, 1, &use_map, lane);
+        m = decode_block<true>(base, ybit + slice_y_length, bits_left - slice_y_length, 2 * ncoef, T, W,
+                               use_map ? W.map[1] : nullptr, P.nb, pc + P.comp_off[1], pc + P.comp_off[2], lut, lane);
+        if (m < 0) bad = true; else maxabs = max(maxabs, m);
+        if (lane == 0) atomicMax(&status[4 * pic + 3], bad ? 0x7fffffff : maxabs);
     }
 }
 
@@ -649,7 +792,12 @@ int vc2b_unpack(const vc2b_params *p, const uint8_t *d_data, const int64_t *d_pi
     if (npictures <= 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
     const long long warps = (long long)npictures * P.slices_x * P.slices_y;
-    const unsigned blocks = (unsigned)((warps + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    // persistent warps, each walking a run of consecutive slices (about 16 CTAs per SM worth of
+    // work items keeps the tail short)
+    const long long max_blocks = 148LL * 64;
+    long long nblk = (warps + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    if (nblk > max_blocks) nblk = max_blocks;
+    const unsigned blocks = (unsigned)nblk;
     if (P.is_ld) {
         ld_init_status_kernel<<<(npictures + 127) / 128, 128, 0, s>>>(P, d_pic_offset, npictures, d_status);
         VC2B_CHECK_LAUNCH();
