@@ -1,0 +1,219 @@
+"""The reference-named drop-in functions (vc2_conformance_b200.pseudocode) against the oracle and
+the golden vectors, on the reference's own containers (nested lists, state dicts)."""
+
+import io
+
+import numpy as np
+import pytest
+
+import synth
+from golden_utils import load
+
+pytestmark = pytest.mark.gpu
+
+ORIENTS = ["HL", "LH", "HH"]
+
+
+def _state(wi, wiho, d, dho, **kw):
+    st = dict(wavelet_index=wi, wavelet_index_ho=wiho, dwt_depth=d, dwt_depth_ho=dho)
+    st.update(kw)
+    return st
+
+
+def _flat_to_dict(p, flat):
+    import oracle as O
+
+    level, orient, w, h, off, total = O.layout(p, 0)
+    d = {}
+    for b in range(len(level)):
+        lv = int(level[b])
+        if lv == 0:
+            nm = "LL" if p.dwt_depth_ho == 0 else "L"
+        elif lv <= p.dwt_depth_ho:
+            nm = "H"
+        else:
+            nm = ORIENTS[int(orient[b]) - 1]
+        d.setdefault(lv, {})[nm] = flat[off[b]: off[b] + w[b] * h[b]].reshape(h[b], w[b]).tolist()
+    return d
+
+
+def test_idwt_dwt_on_reference_containers():
+    """tests/pseudocode/test_picture_encoding.py:113-142 style, against golden transform vectors."""
+    import oracle as O
+    from vc2_conformance_b200 import pseudocode as P
+
+    z = load("transform")
+    for k in range(int(z["count"][0])):
+        wi, wiho, d, dho, W, H = [int(v) for v in z["case_%d" % k]]
+        p = O.make_params(W, H, wavelet_index=wi, wavelet_index_ho=wiho, dwt_depth=d, dwt_depth_ho=dho)
+        st = _state(wi, wiho, d, dho)
+        pic = P.idwt(st, _flat_to_dict(p, z["coeffs_%d" % k]))
+        assert isinstance(pic, list) and isinstance(pic[0][0], int)
+        assert (np.array(pic) == z["idwt_%d" % k]).all(), k
+        co = P.dwt(st, z["pic_%d" % k].tolist())
+        exp = _flat_to_dict(p, z["dwt_%d" % k])
+        assert co == exp, k
+
+
+@pytest.mark.parametrize("wi", [0, 1, 4, 5, 6])
+def test_single_level_synthesis_analysis(wi):
+    """h_/vh_ round trips on the 16x32 ramp a[y][x] = 100y + x (test_picture_encoding.py:79-110)."""
+    from vc2_conformance_b200 import pseudocode as P
+
+    st = _state(wi, wi, 1, 1)
+    a = [[100 * y + x for x in range(32)] for y in range(16)]
+    L, H = P.h_analysis(st, [row[:] for row in a])
+    assert P.h_synthesis(st, L, H) == a
+    LL, HL, LH, HH = P.vh_analysis(st, [row[:] for row in a])
+    assert P.vh_synthesis(st, LL, HL, LH, HH) == a
+
+
+def test_offset_clip_in_place():
+    """tests/pseudocode/test_picture_encoding.py:194-226 (offset invertibility) + clip."""
+    from vc2_conformance_b200 import pseudocode as P
+
+    st = dict(luma_depth=8, color_diff_depth=10)
+    pic = {"Y": [[-200, -128, 0, 127, 300]], "C1": [[-600, -512, 511, 700]], "C2": [[1, 2, 3, 4]]}
+    P.clip_picture(st, pic)
+    assert pic["Y"] == [[-128, -128, 0, 127, 127]] and pic["C1"] == [[-512, -512, 511, 511]]
+    P.offset_picture(st, pic)
+    assert pic["Y"] == [[0, 0, 128, 255, 255]] and pic["C2"] == [[513, 514, 515, 516]]
+    P.remove_offset_picture(st, pic)
+    assert pic["Y"] == [[-128, -128, 0, 127, 127]]
+
+
+def test_quant_scalars():
+    from vc2_conformance_b200 import pseudocode as P
+
+    # tests/pseudocode/test_quantization.py:7-13
+    for n in range(-100, 100, 7):
+        assert abs(n - P.inverse_quant(P.forward_quant(n, 12), 12)) < 8
+    assert P.forward_quant(-9, 4) == -4 and P.inverse_quant(-4, 4) == -9
+    with pytest.raises(P.EnvelopeError):
+        P.inverse_quant(1 << 20, 120)
+
+
+def test_dc_prediction_in_place():
+    from vc2_conformance_b200 import pseudocode as P
+
+    z = load("dc_prediction")
+    for k in range(int(z["count"][0])):
+        band = z["in_%d" % k].tolist()
+        P.dc_prediction(band)
+        assert band == z["pred_%d" % k].tolist()
+        band = z["in_%d" % k].tolist()
+        P.apply_dc_prediction(band)
+        assert band == z["apply_%d" % k].tolist()
+
+
+def _decoder_state(p, qm, data):
+    """A reference-shaped state dict positioned at the start of transform_data (init_io done)."""
+    f = io.BytesIO(data + b"\xAB\xCD")  # two bytes of the next data unit follow
+    first = f.read(1)
+    st = dict(
+        parse_code=0xC8 if p.is_ld else 0xE8, luma_width=p.luma_width, luma_height=p.luma_height,
+        color_diff_width=p.color_diff_width, color_diff_height=p.color_diff_height,
+        luma_depth=p.luma_depth, color_diff_depth=p.color_diff_depth, wavelet_index=p.wavelet_index,
+        wavelet_index_ho=p.wavelet_index_ho, dwt_depth=p.dwt_depth, dwt_depth_ho=p.dwt_depth_ho,
+        slices_x=p.slices_x, slices_y=p.slices_y, quant_matrix=qm, picture_number=7,
+        slice_prefix_bytes=p.slice_prefix_bytes, slice_size_scaler=p.slice_size_scaler,
+        slice_bytes_numerator=p.slice_bytes_numerator, slice_bytes_denominator=p.slice_bytes_denominator,
+        _file=f, current_byte=bytearray(first)[0], next_bit=7,
+        video_parameters={}, picture_coding_mode=0,
+    )
+    return st, f
+
+
+def _qm_dict(a, d, dho):
+    qm = {}
+    if dho == 0:
+        qm[0] = {"LL": int(a[0][0])}
+    else:
+        qm[0] = {"L": int(a[0][0])}
+        for level in range(1, dho + 1):
+            qm[level] = {"H": int(a[level][1])}
+    for level in range(dho + 1, dho + d + 1):
+        qm[level] = {"HL": int(a[level][1]), "LH": int(a[level][2]), "HH": int(a[level][3])}
+    return qm
+
+
+@pytest.mark.parametrize("name", ["hq_lossy_legall_d3", "hq_lossy_dd97_d2_prefix_scaler", "ld_lossy_legall_uneven",
+                                  "hq_lossy_fidelity_daub_asym"])
+def test_transform_data_and_picture_decode_entry_points(name):
+    """The two per-picture entry points the reference's decoder calls (decoder/stream.py:128-133),
+    on a reference-shaped state: reader position, quantizer, current_picture and the callback."""
+    from vc2_conformance_b200 import pseudocode as P
+    from vc2_conformance_b200.params import params_from_arrays
+
+    z = load("pictures")
+    p = params_from_arrays(z[name + ".params"], z[name + ".quant_matrix"])
+    qm = _qm_dict(z[name + ".quant_matrix"], p.dwt_depth, p.dwt_depth_ho)
+    data = z[name + ".data"].tobytes()
+    st, f = _decoder_state(p, qm, data)
+    got = []
+    st["_output_picture_callback"] = lambda pic, vp, pcm: got.append(pic)
+    P.transform_data(st)
+    # reader exactly after the last slice (decoder/io.py:138 tell semantics)
+    assert st["current_byte"] == 0xAB and st["next_bit"] == 7 and f.tell() == len(data) + 1
+    # lazily materialised reference view of the coefficients
+    lvl0 = "LL" if p.dwt_depth_ho == 0 else "L"
+    band0 = np.array(st["y_transform"][0][lvl0])
+    exp0 = z[name + ".dec_coeffs0"][: band0.size].reshape(band0.shape)
+    assert (band0 == exp0).all()
+    assert st["quantizer"][0][lvl0] == max(int(z[name + ".qindex"][-1]) - qm[0][lvl0], 0)
+    P.picture_decode(st)
+    assert got and got[0]["pic_num"] == 7
+    for c, key in enumerate(["Y", "C1", "C2"]):
+        assert (np.array(got[0][key]) == z[name + ".decoded%d" % c]).all(), (name, key)
+    # and from plain nested dictionaries (a state filled by the reference's own transform_data)
+    st2 = dict(st)
+    for key in ("y_transform", "c1_transform", "c2_transform"):
+        st2[key] = {lv: {o: [row[:] for row in band] for o, band in orients.items()}
+                    for lv, orients in st[key].items()}
+    got.clear()
+    P.picture_decode(st2)
+    for c, key in enumerate(["Y", "C1", "C2"]):
+        assert (np.array(got[0][key]) == z[name + ".decoded%d" % c]).all(), (name, key, "dict")
+
+
+def test_transform_data_raises_on_truncated_stream():
+    from vc2_conformance_b200 import pseudocode as P
+    from vc2_conformance_b200.params import params_from_arrays
+
+    z = load("pictures")
+    name = "hq_lossy_legall_d3"
+    p = params_from_arrays(z[name + ".params"], z[name + ".quant_matrix"])
+    qm = _qm_dict(z[name + ".quant_matrix"], p.dwt_depth, p.dwt_depth_ho)
+    data = z[name + ".data"].tobytes()[:700]
+    st, f = _decoder_state(p, qm, data[:-2])
+    f.seek(0)
+    f.truncate(len(data) - 2)
+    f.seek(1)
+    with pytest.raises(Exception) as ei:
+        P.transform_data(st)
+    assert "EndOfStream" in type(ei.value).__name__ or "EndOfStream" in str(ei.value)
+
+
+def test_picture_encode_entry_point():
+    from vc2_conformance_b200 import pseudocode as P
+    from vc2_conformance_b200.params import params_from_arrays
+
+    z = load("pictures")
+    name = "hq_padded_dims"
+    p = params_from_arrays(z[name + ".params"], z[name + ".quant_matrix"])
+    import oracle as O
+
+    po = synth.oracle_params(p)
+    st = dict(luma_width=p.luma_width, luma_height=p.luma_height, color_diff_width=p.color_diff_width,
+              color_diff_height=p.color_diff_height, luma_depth=p.luma_depth, color_diff_depth=p.color_diff_depth,
+              wavelet_index=p.wavelet_index, wavelet_index_ho=p.wavelet_index_ho, dwt_depth=p.dwt_depth,
+              dwt_depth_ho=p.dwt_depth_ho)
+    pic = {k: z[name + ".pic%d" % c].astype(np.int64).tolist() for c, k in enumerate(["Y", "C1", "C2"])}
+    P.picture_encode(st, pic)
+    for c, key in enumerate(["y_transform", "c1_transform", "c2_transform"]):
+        level, orient, w, h, off, total = O.layout(po, c)
+        exp = z[name + ".enc_coeffs%d" % c]
+        band = np.array(st[key][0]["LL"])
+        assert (band.reshape(-1) == exp[: band.size]).all()
+        last = np.array(st[key][p.dwt_depth]["HH"])
+        assert (last.reshape(-1) == exp[off[-1]:]).all()
