@@ -60,6 +60,12 @@ WORKLOADS = {
         params=dict(luma_width=1920, luma_height=1080, luma_depth=12, wavelet_index=5, wavelet_index_ho=6,
                     dwt_depth=2, dwt_depth_ho=3, slices_x=60, slices_y=270),
         pictures=120, bits_per_sample=3.0),
+    # BASELINE.json configs[4] (encoder path; used by tools/bench_stage.py dwt / quant)
+    "cfg5": dict(
+        name="7680x4320 12-bit 4:4:4 HQ encoder path, Deslauriers-Dubuc(9,7) depth 4, 240x270 slices",
+        params=dict(luma_width=7680, luma_height=4320, luma_depth=12, wavelet_index=0, dwt_depth=4,
+                    slices_x=240, slices_y=270),
+        pictures=8, bits_per_sample=3.0),
 }
 
 

@@ -40,9 +40,12 @@ def run_walk():
     L.vc2b_hq_slice_offsets(C.byref(p), _ptr(codec.data), _ptr(codec.pic_offset), NP, _ptr(codec.slice_offset), _ptr(codec.status), sp)
 def run_quant():
     codec.quantize_device(NP, w["picture_bytes"])
-fn = {"idwt": run_idwt, "dwt": run_dwt, "unpack": run_unpack, "walk": run_walk, "quant": run_quant}[a.stage]
+def run_pack():
+    codec.pack_device(NP, w["picture_bytes"])
+fn = {"idwt": run_idwt, "dwt": run_dwt, "unpack": run_unpack, "walk": run_walk, "quant": run_quant, "pack": run_pack}[a.stage]
 nbytes = {"idwt": (4 * padded + 2 * S) * NP, "dwt": (4 * padded + 2 * S) * NP,
-          "unpack": int(offs[NP]) + 4 * padded * NP, "walk": int(offs[NP]), "quant": 4 * padded * NP}[a.stage]
+          "unpack": int(offs[NP]) + 4 * padded * NP, "walk": int(offs[NP]), "quant": 4 * padded * NP,
+          "pack": int(offs[NP]) + 4 * padded * NP}[a.stage]
 for _ in range(3):
     fn()
 torch.cuda.synchronize()

@@ -155,6 +155,98 @@ __device__ int slice_bits(const SliceBands &T, int nb, const int32_t *__restrict
     return sum - (ncoef - 1 - last);  // trailing zeros are free
 }
 
+// ---- slice staged in shared memory ------------------------------------------------------------
+// The bisection probes every coefficient of the slice ~8 times; gathering the slice once (in
+// bitstream order, with each coefficient's band) makes a probe a pure shared-memory pass.
+constexpr int kStageMax = 2048;  // coefficients (all components) of a slice that fit the staging buffer
+
+struct SliceStage {
+    int32_t coef[kStageMax];     // bitstream order: Y, then C1, C2 (HQ) or C1/C2 interleaved (LD)
+    uint8_t band[kStageMax];
+    uint32_t qf[kMaxBands];      // per probe: quant_factor of each band (saturated)
+    uint32_t rcp[kMaxBands];     // floor((2^32-1) / qf)
+};
+
+__device__ __forceinline__ void stage_slice(const DevParams &P, const SliceBands &TY, const SliceBands &TC,
+                                            const int32_t *__restrict__ pc, int ny, int nc, SliceStage &S, int lane)
+{
+    const int32_t *cy = pc + P.comp_off[0], *c1 = pc + P.comp_off[1], *c2 = pc + P.comp_off[2];
+    for (int j = lane; j < ny; j += 32) {
+        int b;
+        S.coef[j] = slice_coeff(TY, P.nb, cy, j, &b);
+        S.band[j] = (uint8_t)b;
+    }
+    if (P.is_ld) {
+        for (int j = lane; j < 2 * nc; j += 32) {
+            int b;
+            S.coef[ny + j] = slice_coeff(TC, P.nb, (j & 1) ? c2 : c1, j >> 1, &b);
+            S.band[ny + j] = (uint8_t)b;
+        }
+    } else {
+        for (int j = lane; j < nc; j += 32) {
+            int b;
+            S.coef[ny + j] = slice_coeff(TC, P.nb, c1, j, &b);
+            S.band[ny + j] = (uint8_t)b;
+            S.coef[ny + nc + j] = slice_coeff(TC, P.nb, c2, j, &b);
+            S.band[ny + nc + j] = (uint8_t)b;
+        }
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void stage_quantisers(const SliceBands &T, int nb, int qindex, SliceStage &S, int lane)
+{
+    __syncwarp();
+    if (lane < nb) {
+        const uint64_t qf = quant_factor_u64(max(qindex - T.qm[lane], 0));
+        const uint32_t q32 = qf > 0xfffffffeull ? 0xffffffffu : (uint32_t)qf;
+        S.qf[lane] = q32;
+        S.rcp[lane] = 0xffffffffu / q32;
+    }
+    __syncwarp();
+}
+
+// forward_quant magnitude with the staged reciprocal: exact floor(4m / qf)
+__device__ __forceinline__ uint32_t staged_quant_mag(const SliceStage &S, int b, int32_t c)
+{
+    const uint32_t m = c < 0 ? (uint32_t)(-(long long)c) : (uint32_t)c;
+    const uint32_t qf = S.qf[b];
+    if (m >= 0x40000000u) return qf == 0xffffffffu ? 0u : (uint32_t)((4ull * m) / qf);  // 4m overflows 32 bits
+    if (qf == 0xffffffffu) return 0u;  // quant_factor >= 2^32 > 4m
+    const uint32_t n = 4u * m;
+    uint32_t q = __umulhi(n, S.rcp[b]);
+    uint32_t r = n - q * qf;
+    while (r >= qf) { q++; r -= qf; }  // at most two corrections
+    return q;
+}
+
+// bits of the three blocks (Y | C1 | C2, or Y | C for LD) of the staged slice at `qindex`
+__device__ __forceinline__ void staged_bits(const SliceStage &S, int n0, int n1, int n2, int lane, int &b0, int &b1,
+                                            int &b2)
+{
+    int sum0 = 0, sum1 = 0, sum2 = 0, last0 = -1, last1 = -1, last2 = -1;
+    const int e0 = n0, e1 = n0 + n1, e2 = n0 + n1 + n2;
+    for (int j = lane; j < e2; j += 32) {
+        const uint32_t q = staged_quant_mag(S, S.band[j], S.coef[j]);
+        const int len = sint_length(q);
+        if (j < e0) { sum0 += len; if (q) last0 = j; }
+        else if (j < e1) { sum1 += len; if (q) last1 = j - e0; }
+        else { sum2 += len; if (q) last2 = j - e1; }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        sum0 += __shfl_xor_sync(0xffffffffu, sum0, d);
+        sum1 += __shfl_xor_sync(0xffffffffu, sum1, d);
+        sum2 += __shfl_xor_sync(0xffffffffu, sum2, d);
+        last0 = max(last0, __shfl_xor_sync(0xffffffffu, last0, d));
+        last1 = max(last1, __shfl_xor_sync(0xffffffffu, last1, d));
+        last2 = max(last2, __shfl_xor_sync(0xffffffffu, last2, d));
+    }
+    b0 = sum0 - (n0 - 1 - last0);  // trailing zeros are free (calculate_coeffs_bits :217)
+    b1 = sum1 - (n1 - 1 - last1);
+    b2 = n2 > 0 ? sum2 - (n2 - 1 - last2) : 0;
+}
+
 struct FitArgs {
     long long total_coeff_bytes;  // HQ: picture_bytes - 4*slices
     int minimum_qindex;
@@ -173,6 +265,7 @@ quantize_fit_kernel(DevParams P, FitArgs F, const int32_t *__restrict__ coeffs, 
                     int32_t *__restrict__ qindex_out, int32_t *__restrict__ bits_out)
 {
     __shared__ SliceBands tabs[kQWarps][2];
+    __shared__ SliceStage stages[kQWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nslices = P.slices_x * P.slices_y;
     const long long gw = (long long)blockIdx.x * kQWarps + warp;
@@ -183,8 +276,11 @@ quantize_fit_kernel(DevParams P, FitArgs F, const int32_t *__restrict__ coeffs, 
     const int32_t *pc = coeffs + (size_t)pic * P.pic_coeffs;
     SliceBands &TY = tabs[warp][0];
     SliceBands &TC = tabs[warp][1];
+    SliceStage &S = stages[warp];
     const int ny = build_slice_bands(P, 0, sx, sy, TY, lane);
     const int nc = build_slice_bands(P, 1, sx, sy, TC, lane);
+    const bool staged = (ny + 2 * nc) <= kStageMax;
+    if (staged) stage_slice(P, TY, TC, pc, ny, nc, S, lane);
 
     long long target, align;
     if (P.is_ld) {
@@ -199,8 +295,18 @@ quantize_fit_kernel(DevParams P, FitArgs F, const int32_t *__restrict__ coeffs, 
 
     int by = 0, bc1 = 0, bc2 = 0;
     auto fits = [&](int q) -> bool {
-        by = slice_bits<false>(TY, P.nb, pc + P.comp_off[0], nullptr, ny, q, lane);
         long long total;
+        if (staged) {  // quant matrices are per band, identical for the three components
+            stage_quantisers(TY, P.nb, q, S, lane);
+            if (P.is_ld) {
+                staged_bits(S, ny, 2 * nc, 0, lane, by, bc1, bc2);
+                return (long long)by + bc1 <= target;
+            }
+            staged_bits(S, ny, nc, nc, lane, by, bc1, bc2);
+            total = ((by + align - 1) / align + (bc1 + align - 1) / align + (bc2 + align - 1) / align) * align;
+            return total <= target;
+        }
+        by = slice_bits<false>(TY, P.nb, pc + P.comp_off[0], nullptr, ny, q, lane);
         if (P.is_ld) {
             bc1 = slice_bits<true>(TC, P.nb, pc + P.comp_off[1], pc + P.comp_off[2], 2 * nc, q, lane);
             bc2 = 0;

@@ -290,6 +290,31 @@ __device__ __forceinline__ void build_lut(uint16_t *lut, int tid, int nthreads)
     }
 }
 
+// Short codes: the first 8 bits of a code window -> the signed value if the whole code (sign bit
+// included) fits in those 8 bits, else -128.  (0 -> "1"; +-1..+-2 -> 4 bits; +-3..+-6 -> 6 bits;
+// +-7..+-14 -> 8 bits: A.4.4 / decoder/io.py:285-313.)
+__device__ __forceinline__ void build_short_lut(int8_t *slut, int tid, int nthreads)
+{
+    for (int e = tid; e < 256; e += nthreads) {
+        int value = 1, pos = 7, result = -128;
+        bool done = false;
+        while (pos >= 0) {
+            const int follow = (e >> pos) & 1;
+            pos--;
+            if (follow) { done = true; break; }
+            if (pos < 0) break;
+            value = (value << 1) | ((e >> pos) & 1);
+            pos--;
+        }
+        if (done) {
+            value -= 1;
+            if (value == 0) result = 0;
+            else if (pos >= 0) result = ((e >> pos) & 1) ? -value : value;
+        }
+        slut[e] = (int8_t)result;
+    }
+}
+
 // 32 bits of the bounded block starting at block bit `bit` (may be >= nbits): stream bits,
 // with ones beyond the end of the block (decoder/io.py:246-252).
 __device__ __forceinline__ uint32_t fetch_word(const uint8_t *__restrict__ base, long long start_bit,
@@ -338,7 +363,7 @@ template <bool INTERLEAVED>
 __device__ int decode_block(const uint8_t *__restrict__ base, long long start_bit, long long nbits,
                             int ncoef, const WarpBands &T, WarpScratch &W, const uint32_t *__restrict__ cmap, int nb,
                             int32_t *__restrict__ out, int32_t *__restrict__ out2,
-                            const uint16_t *__restrict__ lut, int lane)
+                            const uint16_t *__restrict__ lut, const int8_t *__restrict__ slut, int lane)
 {
     int state_in = 0;
     int produced = 0;
@@ -411,7 +436,11 @@ __device__ int decode_block(const uint8_t *__restrict__ base, long long start_bi
             uint32_t mag = 0;
             int neg = 0;
             const uint32_t f = hi & 0xAAAAAAAAu;
-            if (f != 0) {  // at most 15 data bits: the whole code sits in 32 bits
+            const int sv = slut[hi >> 24];
+            if (sv != -128) {  // the common case: the whole code within 8 bits
+                mag = (uint32_t)(sv < 0 ? -sv : sv);
+                neg = sv < 0;
+            } else if (f != 0) {  // at most 15 data bits: the whole code sits in 32 bits
                 k = __clz(f) >> 1;
                 if (k != 0) {
                     uint32_t v = hi >> (32 - 2 * k);
@@ -486,10 +515,18 @@ __device__ __forceinline__ int build_bands(const DevParams &P, int comp, int sx,
     __syncwarp();
     if (lane < nb) {
         const Band &B = P.band[comp][lane];
-        int x1 = (int)(((long long)B.w * sx) / P.slices_x);
-        int x2 = (int)(((long long)B.w * (sx + 1)) / P.slices_x);
-        int y1 = (int)(((long long)B.h * sy) / P.slices_y);
-        int y2 = (int)(((long long)B.h * (sy + 1)) / P.slices_y);
+        int x1, x2, y1, y2;
+        if ((unsigned)B.w < 32768u && (unsigned)B.h < 32768u && P.slices_x < 65536 && P.slices_y < 65536) {
+            x1 = (int)(((unsigned)B.w * (unsigned)sx) / (unsigned)P.slices_x);
+            x2 = (int)(((unsigned)B.w * (unsigned)(sx + 1)) / (unsigned)P.slices_x);
+            y1 = (int)(((unsigned)B.h * (unsigned)sy) / (unsigned)P.slices_y);
+            y2 = (int)(((unsigned)B.h * (unsigned)(sy + 1)) / (unsigned)P.slices_y);
+        } else {
+            x1 = (int)(((long long)B.w * sx) / P.slices_x);
+            x2 = (int)(((long long)B.w * (sx + 1)) / P.slices_x);
+            y1 = (int)(((long long)B.h * sy) / P.slices_y);
+            y2 = (int)(((long long)B.h * (sy + 1)) / P.slices_y);
+        }
         int q = max(qindex - B.qm, 0);
         T.w[lane] = max(x2 - x1, 1);
         T.h[lane] = y2 - y1;
@@ -538,9 +575,11 @@ unpack_hq_kernel(DevParams P, const uint8_t *__restrict__ data, const int64_t *_
                  int32_t *__restrict__ qindex_out, int32_t *__restrict__ status)
 {
     __shared__ uint16_t lut[1024];
+    __shared__ int8_t slut[256];
     __shared__ WarpBands tabs[kWarpsPerBlock];
     __shared__ WarpScratch scratch[kWarpsPerBlock];
     build_lut(lut, threadIdx.x, blockDim.x);
+    build_short_lut(slut, threadIdx.x, blockDim.x);
     if ((threadIdx.x & 31) == 0) tabs[threadIdx.x >> 5].map_valid[0] = tabs[threadIdx.x >> 5].map_valid[1] = 0;
     __syncthreads();
 
@@ -556,7 +595,7 @@ unpack_hq_kernel(DevParams P, const uint8_t *__restrict__ data, const int64_t *_
                                ((long long)gridDim.x * kWarpsPerBlock);
     const long long gw0 = ((long long)blockIdx.x * kWarpsPerBlock + warp) * per_warp;
     for (long long gw = gw0; gw < gw0 + per_warp && gw < total_slices; gw++) {
-        const int pic = (int)(gw / nslices);
+        const int pic = total_slices < 0x7fffffffLL ? (int)((unsigned)gw / (unsigned)nslices) : (int)(gw / nslices);
         const int n = (int)(gw - (long long)pic * nslices);
         const int sy = n / P.slices_x, sx = n - sy * P.slices_x;
         const uint32_t off = slice_offset[gw];
@@ -577,7 +616,7 @@ unpack_hq_kernel(DevParams P, const uint8_t *__restrict__ data, const int64_t *_
             // luma and chroma rectangles differ: the map is tagged with the component class
             const int ncoef = build_bands(P, c, sx, sy, qindex, T, W, c == 0 ? 0 : 1, &use_map, lane);
             int m = decode_block<false>(base, pos * 8, 8 * length, ncoef, T, W, use_map ? W.map[c == 0 ? 0 : 1] : nullptr,
-                                        P.nb, pc + P.comp_off[c], nullptr, lut, lane);
+                                        P.nb, pc + P.comp_off[c], nullptr, lut, slut, lane);
             if (m < 0) bad = true; else maxabs = max(maxabs, m);
             pos += length;
         }
@@ -592,9 +631,11 @@ unpack_ld_kernel(DevParams P, const uint8_t *__restrict__ data, const int64_t *_
                  int32_t *__restrict__ status)
 {
     __shared__ uint16_t lut[1024];
+    __shared__ int8_t slut[256];
     __shared__ WarpBands tabs[kWarpsPerBlock];
     __shared__ WarpScratch scratch[kWarpsPerBlock];
     build_lut(lut, threadIdx.x, blockDim.x);
+    build_short_lut(slut, threadIdx.x, blockDim.x);
     if ((threadIdx.x & 31) == 0) tabs[threadIdx.x >> 5].map_valid[0] = tabs[threadIdx.x >> 5].map_valid[1] = 0;
     __syncthreads();
 
@@ -608,7 +649,7 @@ unpack_ld_kernel(DevParams P, const uint8_t *__restrict__ data, const int64_t *_
                                ((long long)gridDim.x * kWarpsPerBlock);
     const long long gw0 = ((long long)blockIdx.x * kWarpsPerBlock + warp) * per_warp;
     for (long long gw = gw0; gw < gw0 + per_warp && gw < total_slices; gw++) {
-        const int pic = (int)(gw / nslices);
+        const int pic = total_slices < 0x7fffffffLL ? (int)((unsigned)gw / (unsigned)nslices) : (int)(gw / nslices);
         const int n = (int)(gw - (long long)pic * nslices);
         const int sy = n / P.slices_x, sx = n - sy * P.slices_x;
         const long long nbytes = pic_offset[pic + 1] - pic_offset[pic];
@@ -638,11 +679,11 @@ unpack_ld_kernel(DevParams P, const uint8_t *__restrict__ data, const int64_t *_
         bool use_map;
         int ncoef = build_bands(P, 0, sx, sy, qindex, T, W, 0, &use_map, lane);
         int m = decode_block<false>(base, ybit, slice_y_length, ncoef, T, W, use_map ? W.map[0] : nullptr, P.nb,
-                                    pc + P.comp_off[0], nullptr, lut, lane);
+                                    pc + P.comp_off[0], nullptr, lut, slut, lane);
         if (m < 0) bad = true; else maxabs = max(maxabs, m);
         ncoef = build_bands(P, 1, sx, sy, qindex, T, W, 1, &use_map, lane);
         m = decode_block<true>(base, ybit + slice_y_length, bits_left - slice_y_length, 2 * ncoef, T, W,
-                               use_map ? W.map[1] : nullptr, P.nb, pc + P.comp_off[1], pc + P.comp_off[2], lut, lane);
+                               use_map ? W.map[1] : nullptr, P.nb, pc + P.comp_off[1], pc + P.comp_off[2], lut, slut, lane);
         if (m < 0) bad = true; else maxabs = max(maxabs, m);
         if (lane == 0) atomicMax(&status[4 * pic + 3], bad ? 0x7fffffff : maxabs);
     }
