@@ -36,6 +36,12 @@ struct AnaArgs {
     int32_t ncomp;
 };
 
+}  // namespace vc2b
+
+#include "dwt8.cuh"
+
+namespace vc2b {
+
 template <int FV, int FH, bool VERT, int TW, int TH>
 __global__ void __launch_bounds__(kDwtThreads)
 dwt_level_kernel(AnaArgs A)
@@ -133,6 +139,9 @@ __global__ void dwt_copy_kernel(AnaArgs A)
 template <int FV, int FH, bool VERT>
 static int launch_ana_t(const AnaArgs &A_in, int npic, cudaStream_t s)
 {
+    if constexpr (VERT && Ana8Cfg<FV, FH>::kSupported && (FV == FH)) {
+        if (ana_is_wide_ok(A_in, npic)) return launch_ana_wide<FV, FH>(A_in, npic, s);
+    }
     constexpr int HX = get_filter(FH).halo;
     constexpr int HY = VERT ? get_filter(FV).halo : 0;
     constexpr int TW = 128;
@@ -160,6 +169,9 @@ static int launch_ana_t(const AnaArgs &A_in, int npic, cudaStream_t s)
 template <int FV, bool VERT>
 static int launch_ana_h(int fh, const AnaArgs &A, int npic, cudaStream_t s)
 {
+#ifdef VC2B_DEV_BUILD
+    return VC2B_E_UNSUPPORTED;
+#else
     switch (fh) {
     case 0: return launch_ana_t<FV, 0, VERT>(A, npic, s);
     case 1: return launch_ana_t<FV, 1, VERT>(A, npic, s);
@@ -168,12 +180,17 @@ static int launch_ana_h(int fh, const AnaArgs &A, int npic, cudaStream_t s)
     case 5: return launch_ana_t<FV, 5, VERT>(A, npic, s);
     default: return launch_ana_t<FV, 6, VERT>(A, npic, s);
     }
+#endif
 }
 
 static int launch_ana(int fv, int fh, bool vert, const AnaArgs &A, int npic, cudaStream_t s)
 {
     if (fv == 4) fv = 3;  // Haar with/without shift: same stages, shift is a runtime argument
     if (fh == 4) fh = 3;
+#ifdef VC2B_DEV_BUILD
+    if (fh != 0 || (vert && fv != 0)) return VC2B_E_UNSUPPORTED;
+    return vert ? launch_ana_t<0, 0, true>(A, npic, s) : launch_ana_t<0, 0, false>(A, npic, s);
+#endif
     if (!vert) return launch_ana_h<0, false>(fh, A, npic, s);
     switch (fv) {
     case 0: return launch_ana_h<0, true>(fh, A, npic, s);

@@ -26,13 +26,23 @@ struct StreamPlan {
     int ring;        // power of two >= back + 1 + prefetch
 };
 
-__host__ __device__ constexpr StreamPlan make_stream_plan(int filter)
+// Stage `sidx` in order of application: synthesis applies the table order; analysis applies the
+// stages reversed with add <-> subtract swapped (pseudocode/picture_encoding.py:203-223).
+__host__ __device__ constexpr StageDef stream_stage(int filter, int sidx, bool analysis)
+{
+    const FilterDef f = get_filter(filter);
+    StageDef st = f.st[analysis ? f.nstages - 1 - sidx : sidx];
+    if (analysis) st.type = analysis_type(st.type);
+    return st;
+}
+
+__host__ __device__ constexpr StreamPlan make_stream_plan(int filter, bool analysis = false)
 {
     const FilterDef f = get_filter(filter);
     StreamPlan p = {};
     p.ns = f.nstages;
     for (int s = 0; s < f.nstages; s++) {
-        const StageDef st = f.st[s];
+        const StageDef st = stream_stage(filter, s, analysis);
         const bool even = (st.type == 1 || st.type == 2);
         p.parity[s] = even ? 0 : 1;
         // even update reads odd sample n+i-1, odd update reads even sample n+i (i in [D, L+D))
@@ -102,11 +112,11 @@ __device__ __forceinline__ void ring_add_dyn(int (&a)[RING], int slot, int d)
 }
 
 // One stage of one step, compile-time slots.  U = (t - ks) mod RING.
-template <int F, int SIDX, int U, int RING, int NC>
+template <int F, int SIDX, int U, int RING, int NC, bool ANA = false>
 __device__ __forceinline__ void vstage_fast(PairRing<RING, NC> &R)
 {
-    constexpr StreamPlan P = make_stream_plan(F);
-    constexpr StageDef st = get_filter(F).st[SIDX];
+    constexpr StreamPlan P = make_stream_plan(F, ANA);
+    constexpr StageDef st = stream_stage(F, SIDX, ANA);
     constexpr int par = P.parity[SIDX];
     constexpr int k = U - P.lag[SIDX];
     constexpr bool add = (st.type == 1 || st.type == 3);
@@ -126,11 +136,11 @@ __device__ __forceinline__ void vstage_fast(PairRing<RING, NC> &R)
 // Same with run-time pair indices and the edge clamps of lift1-4 (picture_decoding.py:210-212,
 // :240-242): a source pair outside [0, last] reads pair 0 / pair `last`.  t is the absolute
 // step; ks the pair stored in slot 0 (slots are (m - ks) mod RING).
-template <int F, int SIDX, int RING, int NC>
+template <int F, int SIDX, int RING, int NC, bool ANA = false>
 __device__ __forceinline__ void vstage_slow(PairRing<RING, NC> &R, int t, int ks, int last)
 {
-    constexpr StreamPlan P = make_stream_plan(F);
-    constexpr StageDef st = get_filter(F).st[SIDX];
+    constexpr StreamPlan P = make_stream_plan(F, ANA);
+    constexpr StageDef st = stream_stage(F, SIDX, ANA);
     constexpr int par = P.parity[SIDX];
     constexpr bool add = (st.type == 1 || st.type == 3);
     const int k = t - P.lag[SIDX];
@@ -150,24 +160,24 @@ __device__ __forceinline__ void vstage_slow(PairRing<RING, NC> &R, int t, int ks
     }
 }
 
-template <int F, int U, int RING, int NC>
+template <int F, int U, int RING, int NC, bool ANA = false>
 __device__ __forceinline__ void vstep_fast(PairRing<RING, NC> &R)
 {
     constexpr int ns = get_filter(F).nstages;
-    vstage_fast<F, 0, U, RING, NC>(R);
-    if constexpr (ns > 1) vstage_fast<F, (ns > 1 ? 1 : 0), U, RING, NC>(R);
-    if constexpr (ns > 2) vstage_fast<F, (ns > 2 ? 2 : 0), U, RING, NC>(R);
-    if constexpr (ns > 3) vstage_fast<F, (ns > 3 ? 3 : 0), U, RING, NC>(R);
+    vstage_fast<F, 0, U, RING, NC, ANA>(R);
+    if constexpr (ns > 1) vstage_fast<F, (ns > 1 ? 1 : 0), U, RING, NC, ANA>(R);
+    if constexpr (ns > 2) vstage_fast<F, (ns > 2 ? 2 : 0), U, RING, NC, ANA>(R);
+    if constexpr (ns > 3) vstage_fast<F, (ns > 3 ? 3 : 0), U, RING, NC, ANA>(R);
 }
 
-template <int F, int RING, int NC>
+template <int F, int RING, int NC, bool ANA = false>
 __device__ __forceinline__ void vstep_slow(PairRing<RING, NC> &R, int t, int ks, int last)
 {
     constexpr int ns = get_filter(F).nstages;
-    vstage_slow<F, 0, RING, NC>(R, t, ks, last);
-    if constexpr (ns > 1) vstage_slow<F, (ns > 1 ? 1 : 0), RING, NC>(R, t, ks, last);
-    if constexpr (ns > 2) vstage_slow<F, (ns > 2 ? 2 : 0), RING, NC>(R, t, ks, last);
-    if constexpr (ns > 3) vstage_slow<F, (ns > 3 ? 3 : 0), RING, NC>(R, t, ks, last);
+    vstage_slow<F, 0, RING, NC, ANA>(R, t, ks, last);
+    if constexpr (ns > 1) vstage_slow<F, (ns > 1 ? 1 : 0), RING, NC, ANA>(R, t, ks, last);
+    if constexpr (ns > 2) vstage_slow<F, (ns > 2 ? 2 : 0), RING, NC, ANA>(R, t, ks, last);
+    if constexpr (ns > 3) vstage_slow<F, (ns > 3 ? 3 : 0), RING, NC, ANA>(R, t, ks, last);
 }
 
 }  // namespace vc2b
