@@ -268,7 +268,7 @@ struct WarpBands {        // per-warp tables in shared memory, rebuilt per slice
 
 struct WarpScratch {
     uint32_t words[kRoundWords + 4];     // the round's words (+ look-ahead for codes that run on)
-    uint16_t pos[kRoundWords * 32];      // start bit (within the round) of every code of the round
+    uint32_t pos[kRoundWords * 8];       // non-zero codes of the round: start bit | index in the round << 16
     uint32_t map[2][kMapMax];            // [luma, chroma]: coefficient index -> band << 26 | y * stride + x
 };
 
@@ -370,6 +370,17 @@ __device__ int decode_block(const uint8_t *__restrict__ base, long long start_bi
     int maxabs = 0;
     bool overflow = false;
 
+    // Most coefficients are zero (a single '1' bit, or nothing at all once the block has run out:
+    // the 1-extension).  Zero the slice's rectangles first with coalesced stores, then only the
+    // non-zero codes are decoded, dequantised and scattered.
+    for (int idx = lane; idx < ncoef; idx += 32) {
+        const int jj = INTERLEAVED ? (idx >> 1) : idx;
+        const uint32_t loc = cmap ? cmap[jj] : locate(T, nb, jj);
+        int32_t *dst = (INTERLEAVED && (idx & 1)) ? out2 : out;
+        dst[T.base[loc >> 26] + (loc & 0x3ffffffu)] = 0;
+    }
+    __syncwarp();
+
     for (long long rbit = 0; produced < ncoef && rbit < nbits; rbit += 32 * kRoundWords) {
         // ---- A: stage the round's words, find every code start ------------------------------
         const uint32_t w0 = fetch_word(base, start_bit, rbit + 32 * lane, nbits);
@@ -403,35 +414,41 @@ __device__ int decode_block(const uint8_t *__restrict__ base, long long start_bi
         if (s_start == 1) mask = mask_sel[1];
         if (s_start == 2) mask = mask_sel[2];
         if (s_start == 3) mask = mask_sel[3];
-        const int mycnt = __popc(mask);
-        int pre = mycnt;
+        // a code whose first bit is 1 is the value zero: only the others need decoding
+        const uint32_t nzmask = mask & ~w0;
+        const int mycnt = __popc(mask), mynz = __popc(nzmask);
+        int pre = mycnt | (mynz << 16);  // both prefix sums in one scan (counts <= 1024)
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             int o = __shfl_up_sync(0xffffffffu, pre, d);
             if (lane >= d) pre += o;
         }
-        const int total = __shfl_sync(0xffffffffu, pre, 31);
+        const int tot = __shfl_sync(0xffffffffu, pre, 31);
+        const int total = tot & 0xffff, total_nz = tot >> 16;
         const int last_map = __shfl_sync(0xffffffffu, inc, 31);
         state_in = (last_map >> (2 * state_in)) & 3;
         {
-            int c = pre - mycnt;
-            uint32_t m = mask;
+            const int c0 = (pre & 0xffff) - mycnt;   // index (in the round) of this word's first code
+            int z = (pre >> 16) - mynz;              // slot of this word's first non-zero code
+            uint32_t m = nzmask;
             while (m) {
                 const int bitpos = __clz(m);  // bit 31 = first bit of the word
-                W.pos[c++] = (uint16_t)(32 * lane + bitpos);
+                const int rank = bitpos ? __popc(mask >> (32 - bitpos)) : 0;  // code starts before it
+                W.pos[z++] = (uint32_t)(32 * lane + bitpos) | ((uint32_t)(c0 + rank) << 16);
                 m &= ~(0x80000000u >> bitpos);
             }
         }
         __syncwarp();
 
-        // ---- B: one code per lane ----------------------------------------------------------------
-        const int ncodes = min(total, ncoef - produced);
-        for (int c = lane; c < ncodes; c += 32) {
-            const int p = W.pos[c];
+        // ---- B: one non-zero code per lane ---------------------------------------------------
+        const int limit = ncoef - produced;  // codes of this round that are coefficients
+        for (int c = lane; c < total_nz; c += 32) {
+            const uint32_t ent = W.pos[c];
+            const int p = ent & 0xffff, ci = ent >> 16;
+            if (ci >= limit) continue;
             const int wi = p >> 5, sh = p & 31;
             const uint32_t a0 = W.words[wi], a1 = W.words[wi + 1];
             const uint32_t hi = __funnelshift_l(a1, a0, sh);
-            int32_t value = 0;
             int k;
             uint32_t mag = 0;
             int neg = 0;
@@ -442,15 +459,13 @@ __device__ int decode_block(const uint8_t *__restrict__ base, long long start_bi
                 neg = sv < 0;
             } else if (f != 0) {  // at most 15 data bits: the whole code sits in 32 bits
                 k = __clz(f) >> 1;
-                if (k != 0) {
-                    uint32_t v = hi >> (32 - 2 * k);
-                    v = (v | (v >> 1)) & 0x33333333u;
-                    v = (v | (v >> 2)) & 0x0f0f0f0fu;
-                    v = (v | (v >> 4)) & 0x00ff00ffu;
-                    v = (v | (v >> 8)) & 0x0000ffffu;
-                    mag = ((1u << k) | v) - 1u;
-                    neg = (hi >> (30 - 2 * k)) & 1;
-                }
+                uint32_t v = hi >> (32 - 2 * k);
+                v = (v | (v >> 1)) & 0x33333333u;
+                v = (v | (v >> 2)) & 0x0f0f0f0fu;
+                v = (v | (v >> 4)) & 0x00ff00ffu;
+                v = (v | (v >> 8)) & 0x0000ffffu;
+                mag = ((1u << k) | v) - 1u;
+                neg = (hi >> (30 - 2 * k)) & 1;
             } else {
                 const uint32_t a2 = W.words[wi + 2];
                 const uint32_t lo = __funnelshift_l(a2, a1, sh);
@@ -458,7 +473,6 @@ __device__ int decode_block(const uint8_t *__restrict__ base, long long start_bi
                 const unsigned long long ff = win & 0xAAAAAAAAAAAAAAAAull;
                 if (ff == 0) {  // 32 or more data bits: outside the int32 envelope
                     overflow = true;
-                    k = 0;
                 } else {
                     k = __clzll((long long)ff) >> 1;
                     unsigned long long v = win >> (64 - 2 * k);
@@ -471,29 +485,18 @@ __device__ int decode_block(const uint8_t *__restrict__ base, long long start_bi
                     neg = (int)((win >> (62 - 2 * k)) & 1);
                 }
             }
-            const int idx = produced + c;
+            const int idx = produced + ci;
             const int jj = INTERLEAVED ? (idx >> 1) : idx;
             const uint32_t loc = cmap ? cmap[jj] : locate(T, nb, jj);
             const int b = loc >> 26;
-            if (mag != 0) {
-                // inverse_quant (pseudocode/quantization.py:18): (m*qf + qo + 2) // 4
-                const unsigned long long t = ((unsigned long long)mag * T.qf[b] + T.qo[b]) >> 2;
-                if (t > 0x7fffffffull || T.qf[b] == 0xffffffffu) overflow = true;
-                value = neg ? -(int32_t)t : (int32_t)t;
-                maxabs = max(maxabs, (int)t);
-            }
+            // inverse_quant (pseudocode/quantization.py:18): (m*qf + qo + 2) // 4
+            const unsigned long long t = ((unsigned long long)mag * T.qf[b] + T.qo[b]) >> 2;
+            if (t > 0x7fffffffull || T.qf[b] == 0xffffffffu) overflow = true;
+            maxabs = max(maxabs, (int)t);
             int32_t *dst = (INTERLEAVED && (idx & 1)) ? out2 : out;
-            dst[T.base[b] + (loc & 0x3ffffffu)] = value;
+            dst[T.base[b] + (loc & 0x3ffffffu)] = neg ? -(int32_t)t : (int32_t)t;
         }
         produced += total;
-    }
-    if (produced > ncoef) produced = ncoef;
-    // everything not reached before the block ran out is zero (code "1" from the 1-extension)
-    for (int idx = produced + lane; idx < ncoef; idx += 32) {
-        const int jj = INTERLEAVED ? (idx >> 1) : idx;
-        const uint32_t loc = cmap ? cmap[jj] : locate(T, nb, jj);
-        int32_t *dst = (INTERLEAVED && (idx & 1)) ? out2 : out;
-        dst[T.base[loc >> 26] + (loc & 0x3ffffffu)] = 0;
     }
     overflow = __any_sync(0xffffffffu, overflow);
 #pragma unroll
