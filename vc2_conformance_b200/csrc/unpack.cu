@@ -509,8 +509,21 @@ __device__ int decode_block(const uint8_t *__restrict__ base, long long start_bi
 // decoder/transform_data_syntax.py:255), and the coefficient -> destination map (reused from
 // the previous slice of this warp when the rectangles have the same dimensions).
 // Returns the number of coefficients; *use_map tells whether W.map is valid for it.
+constexpr int kQTab = 256;  // quantisers 0..255 (qindex is at most 8 bits)
+
+// quant_factor / quant_offset + 2 of every quantiser (pseudocode/quantization.py:40-62), saturated
+__device__ __forceinline__ void build_qtab(uint2 *qtab, int tid, int nthreads)
+{
+    for (int q = tid; q < kQTab; q += nthreads) {
+        const uint64_t qf = quant_factor_u64(q);
+        qtab[q] = qf > 0xfffffffeull ? make_uint2(0xffffffffu, 0u)
+                                      : make_uint2((uint32_t)qf, (uint32_t)quant_offset_u64(q) + 2u);
+    }
+}
+
 __device__ __forceinline__ int build_bands(const DevParams &P, int comp, int sx, int sy, int qindex,
-                                           WarpBands &T, WarpScratch &W, int map_id, bool *use_map, int lane)
+                                           WarpBands &T, WarpScratch &W, const uint2 *__restrict__ qtab, int map_id,
+                                           bool *use_map, int lane)
 {
     const int nb = P.nb;
     int cnt = 0;
@@ -535,9 +548,9 @@ __device__ __forceinline__ int build_bands(const DevParams &P, int comp, int sx,
         T.h[lane] = y2 - y1;
         T.stride[lane] = B.w;
         T.base[lane] = B.off + y1 * B.w + x1;
-        const uint64_t qf = quant_factor_u64(q);
-        T.qf[lane] = qf > 0xfffffffeull ? 0xffffffffu : (uint32_t)qf;
-        T.qo[lane] = qf > 0xfffffffeull ? 0u : (uint32_t)quant_offset_u64(q) + 2u;
+        const uint2 qq = qtab[min(q, kQTab - 1)];
+        T.qf[lane] = qq.x;
+        T.qo[lane] = qq.y;
         cnt = (x2 - x1) * (y2 - y1);
         same = T.map_valid[map_id] && (T.map_w[map_id][lane] == x2 - x1) && (T.map_h[map_id][lane] == y2 - y1);
         T.map_w[map_id][lane] = x2 - x1;
@@ -581,8 +594,10 @@ unpack_hq_kernel(DevParams P, const uint8_t *__restrict__ data, const int64_t *_
     __shared__ int8_t slut[256];
     __shared__ WarpBands tabs[kWarpsPerBlock];
     __shared__ WarpScratch scratch[kWarpsPerBlock];
+    __shared__ uint2 qtab[kQTab];
     build_lut(lut, threadIdx.x, blockDim.x);
     build_short_lut(slut, threadIdx.x, blockDim.x);
+    build_qtab(qtab, threadIdx.x, blockDim.x);
     if ((threadIdx.x & 31) == 0) tabs[threadIdx.x >> 5].map_valid[0] = tabs[threadIdx.x >> 5].map_valid[1] = 0;
     __syncthreads();
 
@@ -617,7 +632,7 @@ unpack_hq_kernel(DevParams P, const uint8_t *__restrict__ data, const int64_t *_
             pos += 1;
             bool use_map;
             // luma and chroma rectangles differ: the map is tagged with the component class
-            const int ncoef = build_bands(P, c, sx, sy, qindex, T, W, c == 0 ? 0 : 1, &use_map, lane);
+            const int ncoef = build_bands(P, c, sx, sy, qindex, T, W, qtab, c == 0 ? 0 : 1, &use_map, lane);
             int m = decode_block<false>(base, pos * 8, 8 * length, ncoef, T, W, use_map ? W.map[c == 0 ? 0 : 1] : nullptr,
                                         P.nb, pc + P.comp_off[c], nullptr, lut, slut, lane);
             if (m < 0) bad = true; else maxabs = max(maxabs, m);
@@ -637,8 +652,10 @@ unpack_ld_kernel(DevParams P, const uint8_t *__restrict__ data, const int64_t *_
     __shared__ int8_t slut[256];
     __shared__ WarpBands tabs[kWarpsPerBlock];
     __shared__ WarpScratch scratch[kWarpsPerBlock];
+    __shared__ uint2 qtab[kQTab];
     build_lut(lut, threadIdx.x, blockDim.x);
     build_short_lut(slut, threadIdx.x, blockDim.x);
+    build_qtab(qtab, threadIdx.x, blockDim.x);
     if ((threadIdx.x & 31) == 0) tabs[threadIdx.x >> 5].map_valid[0] = tabs[threadIdx.x >> 5].map_valid[1] = 0;
     __syncthreads();
 
@@ -680,11 +697,11 @@ unpack_ld_kernel(DevParams P, const uint8_t *__restrict__ data, const int64_t *_
         int maxabs = 0;
         bool bad = false;
         bool use_map;
-        int ncoef = build_bands(P, 0, sx, sy, qindex, T, W, 0, &use_map, lane);
+        int ncoef = build_bands(P, 0, sx, sy, qindex, T, W, qtab, 0, &use_map, lane);
         int m = decode_block<false>(base, ybit, slice_y_length, ncoef, T, W, use_map ? W.map[0] : nullptr, P.nb,
                                     pc + P.comp_off[0], nullptr, lut, slut, lane);
         if (m < 0) bad = true; else maxabs = max(maxabs, m);
-        ncoef = build_bands(P, 1, sx, sy, qindex, T, W, 1, &use_map, lane);
+        ncoef = build_bands(P, 1, sx, sy, qindex, T, W, qtab, 1, &use_map, lane);
         m = decode_block<true>(base, ybit + slice_y_length, bits_left - slice_y_length, 2 * ncoef, T, W,
                                use_map ? W.map[1] : nullptr, P.nb, pc + P.comp_off[1], pc + P.comp_off[2], lut, slut, lane);
         if (m < 0) bad = true; else maxabs = max(maxabs, m);
