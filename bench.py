@@ -80,7 +80,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--chunk", type=int, default=8)
-    ap.add_argument("--group", type=int, default=32, help="pictures per IDWT launch group")
+    ap.add_argument("--group", type=int, default=128, help="pictures per IDWT launch group")
     return ap.parse_args()
 
 

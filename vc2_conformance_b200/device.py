@@ -49,7 +49,7 @@ class BatchCodec(object):
     """Buffers and launch sequence for batches of up to ``max_pictures`` pictures that share one
     parameter set.  All device work is enqueued on ``stream`` (default: torch's current)."""
 
-    def __init__(self, params, max_pictures, max_stream_bytes=None, device="cuda:0", group=32):
+    def __init__(self, params, max_pictures, max_stream_bytes=None, device="cuda:0", group=128):
         torch = _torch()
         self.torch = torch
         self.lib = capi.lib()
