@@ -69,6 +69,16 @@ WORKLOADS = {
 }
 
 
+# DRAM traffic per picture (dram__bytes_read.sum + dram__bytes_write.sum) from `ncu --set full`
+# captures of these kernels on this workload; the summaries are committed under profiles/.
+NCU_TRAFFIC_PER_PICTURE = {
+    "cfg2": {
+        "unpack": (87.2e6, "profiles/r1_v5_unpack_ncu_full_raw.csv (unpack_hq_kernel, 64 pictures)"),
+        "idwt": (144.0e6, "profiles/r1_v4_idwt_levels_ncu.csv (4 idwt_stream8_kernel launches, 16 pictures)"),
+    },
+}
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -466,8 +476,13 @@ def run_ours(args):
                             % (p.dwt_depth + p.dwt_depth_ho)},
     }
     dom = "unpack" if ms_unpack >= ms_idwt else "idwt"
+    traffic, traffic_src = None, None
+    if args.workload in NCU_TRAFFIC_PER_PICTURE and dom in NCU_TRAFFIC_PER_PICTURE[args.workload]:
+        per_pic, traffic_src = NCU_TRAFFIC_PER_PICTURE[args.workload][dom]
+        traffic = per_pic * NP  # per launch of the stage, like `achieved`
     roofline = {"bound": "hbm", "stage": dom, "achieved": stages[dom]["achieved"], "peak": peak, "unit": "GB/s",
-                "frac": stages[dom]["frac"], "traffic": None, "peak_source": peak_src}
+                "frac": stages[dom]["frac"], "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes": stages[dom]["algorithmic_bytes_per_picture"] * NP, "peak_source": peak_src}
 
     # ---- CPU baseline (rank 0, N=1 only) -------------------------------------------------------
     cpu = None
