@@ -11,7 +11,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("stage")
 ap.add_argument("--workload", default="cfg2")
 ap.add_argument("--pictures", type=int, default=16)
-ap.add_argument("--group", type=int, default=4)
+ap.add_argument("--group", type=int, default=128)
 ap.add_argument("--iters", type=int, default=10)
 a = ap.parse_args()
 w = bench.make_workload(a.workload, a.pictures)

@@ -19,7 +19,9 @@ struct Ana8Cfg {
     static constexpr int NP = kWideNP;
     static constexpr StreamPlan P = make_stream_plan(FV, true);
     static constexpr StreamPlan PH = make_stream_plan(FH, true);
-    static constexpr int RING = P.back + 1 <= 4 ? 4 : (P.back + 1 <= 8 ? 8 : 16);
+    static constexpr int RING = P.window <= 4 ? 4 : (P.window <= 8 ? 8 : 16);
+    static constexpr int EMAX = P.entry[0] > P.entry[1] ? P.entry[0] : P.entry[1];
+    static constexpr int STAGES = 4 + EMAX;
     static constexpr int STEPS = STEPS_;
     static constexpr int RSP = STEPS - P.warm - P.maxlag;
     static constexpr int HLQ = (get_filter(FH).halo + 2 * NP - 1) / (2 * NP);
@@ -40,11 +42,12 @@ struct Ana8Ctx {
     int32_t *ll, *b0, *b1, *b2;  // outputs, row stride W / 2
 };
 
-// stage pair m: rows 2m, 2m+1 of this lane's 2*NP columns
+// stage pair m: rows 2m, 2m+1 of this lane's 2*NP columns (NS stage slots)
+template <int NS>
 __device__ __forceinline__ void ana_stage_pair(const Ana8Ctx &X, WideVec *smem, int m)
 {
     constexpr int NC = kWideNC;
-    WideVec *st = smem + ((m & (kWideStages - 1)) * 4) * 32 + X.lane;
+    WideVec *st = smem + ((((m % NS) + NS) % NS) * 4) * 32 + X.lane;
     const int r0 = min(max(2 * m, 0), 2 * X.h2 - 1), r1 = min(max(2 * m + 1, 0), 2 * X.h2 - 1);
     if (X.from_u16) {
         // 2*NP uint16 = one vector per row; rows beyond the picture replicate the last row
@@ -68,16 +71,20 @@ __device__ __forceinline__ void ana_stage_pair(const Ana8Ctx &X, WideVec *smem, 
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-// fetch the two rows of pair m as (E, O) column-parity arrays, offset removed and pre-shifted
-__device__ __forceinline__ void ana_load_pair(const Ana8Ctx &X, const WideVec *smem, int m, int (&E0)[kWideNP],
+// At step t: the even row of pair t - EV0 and the odd row of pair t - EV1 as (E, O) column-parity
+// arrays, offset removed and pre-shifted
+template <int NS, int EV0, int EV1>
+__device__ __forceinline__ void ana_load_pair(const Ana8Ctx &X, const WideVec *smem, int t, int (&E0)[kWideNP],
                                               int (&O0)[kWideNP], int (&E1)[kWideNP], int (&O1)[kWideNP])
 {
     constexpr int NP = kWideNP, NC = kWideNC;
-    asm volatile("cp.async.wait_group %0;" ::"n"(kWideStages - 1) : "memory");
-    const WideVec *st = smem + ((m & (kWideStages - 1)) * 4) * 32 + X.lane;
+    asm volatile("cp.async.wait_group %0;" ::"n"(3) : "memory");
+    const int me = t - EV0, mo = t - EV1;
+    const WideVec *se = smem + ((((me % NS) + NS) % NS) * 4) * 32 + X.lane;
+    const WideVec *so = smem + ((((mo % NS) + NS) % NS) * 4) * 32 + X.lane;
     int row0[NC], row1[NC];
     if (X.from_u16) {
-        const WideVec a = st[0], b = st[32];
+        const WideVec a = se[0], b = so[32];
         const uint32_t wa[4] = {(uint32_t)a.x, (uint32_t)a.y, (uint32_t)a.z, (uint32_t)a.w};
         const uint32_t wb[4] = {(uint32_t)b.x, (uint32_t)b.y, (uint32_t)b.z, (uint32_t)b.w};
 #pragma unroll
@@ -88,7 +95,7 @@ __device__ __forceinline__ void ana_load_pair(const Ana8Ctx &X, const WideVec *s
             row1[2 * i + 1] = (int)(wb[i] >> 16) - X.half;
         }
         if (X.pad_lane) {  // dwt_pad_addition: columns past the picture replicate its last column
-            const int r0 = min(max(2 * m, 0), 2 * X.h2 - 1), r1 = min(max(2 * m + 1, 0), 2 * X.h2 - 1);
+            const int r0 = min(max(2 * me, 0), 2 * X.h2 - 1), r1 = min(max(2 * mo + 1, 0), 2 * X.h2 - 1);
             const int y0 = min(r0, X.pic_h - 1), y1 = min(r1, X.pic_h - 1);
 #pragma unroll
             for (int i = 0; i < NC; i++) {
@@ -98,19 +105,19 @@ __device__ __forceinline__ void ana_load_pair(const Ana8Ctx &X, const WideVec *s
             }
         }
     } else {
-        int t[NP];
-        vec_to_array(st[0], t);
+        int tmp[NP];
+        vec_to_array(se[0], tmp);
 #pragma unroll
-        for (int i = 0; i < NP; i++) row0[i] = t[i];
-        vec_to_array(st[32], t);
+        for (int i = 0; i < NP; i++) row0[i] = tmp[i];
+        vec_to_array(se[32], tmp);
 #pragma unroll
-        for (int i = 0; i < NP; i++) row0[NP + i] = t[i];
-        vec_to_array(st[64], t);
+        for (int i = 0; i < NP; i++) row0[NP + i] = tmp[i];
+        vec_to_array(so[64], tmp);
 #pragma unroll
-        for (int i = 0; i < NP; i++) row1[i] = t[i];
-        vec_to_array(st[96], t);
+        for (int i = 0; i < NP; i++) row1[i] = tmp[i];
+        vec_to_array(so[96], tmp);
 #pragma unroll
-        for (int i = 0; i < NP; i++) row1[NP + i] = t[i];
+        for (int i = 0; i < NP; i++) row1[NP + i] = tmp[i];
     }
 #pragma unroll
     for (int i = 0; i < NP; i++) {
@@ -122,15 +129,16 @@ __device__ __forceinline__ void ana_load_pair(const Ana8Ctx &X, const WideVec *s
 }
 
 template <int RING>
-__device__ __forceinline__ void ana_put(PairRing<RING, kWideNC> &R, int slot, const int (&E0)[kWideNP],
-                                        const int (&O0)[kWideNP], const int (&E1)[kWideNP], const int (&O1)[kWideNP])
+__device__ __forceinline__ void ana_put(PairRing<RING, kWideNC> &R, int slot_even, int slot_odd,
+                                        const int (&E0)[kWideNP], const int (&O0)[kWideNP], const int (&E1)[kWideNP],
+                                        const int (&O1)[kWideNP])
 {
 #pragma unroll
     for (int i = 0; i < kWideNP; i++) {
-        R.v[0][2 * i][slot] = E0[i];
-        R.v[0][2 * i + 1][slot] = O0[i];
-        R.v[1][2 * i][slot] = E1[i];
-        R.v[1][2 * i + 1][slot] = O1[i];
+        R.v[0][2 * i][slot_even] = E0[i];
+        R.v[0][2 * i + 1][slot_even] = O0[i];
+        R.v[1][2 * i][slot_odd] = E1[i];
+        R.v[1][2 * i + 1][slot_odd] = O1[i];
     }
 }
 
@@ -152,15 +160,16 @@ __device__ __forceinline__ void ana_step_fast(PairRing<Ana8Cfg<FV, FH>::RING, kW
 {
     using C = Ana8Cfg<FV, FH>;
     constexpr int RING = C::RING, M = RING - 1;
+    constexpr int EV0 = C::P.entry[0], EV1 = C::P.entry[1], NS = C::STAGES;
     {
         int E0[kWideNP], O0[kWideNP], E1[kWideNP], O1[kWideNP];
-        ana_load_pair(X, smem, t, E0, O0, E1, O1);
+        ana_load_pair<NS, EV0, EV1>(X, smem, t, E0, O0, E1, O1);
         hlift8<FH, true, Ana8Ctx>(E0, O0, X);
         hlift8<FH, true, Ana8Ctx>(E1, O1, X);
-        ana_put<RING>(R, U & M, E0, O0, E1, O1);
+        ana_put<RING>(R, (U - EV0) & M, (U - EV1) & M, E0, O0, E1, O1);
     }
     vstep_fast<FV, U, RING, kWideNC, true>(R);
-    ana_stage_pair(X, smem, t + kWideStages);
+    ana_stage_pair<NS>(X, smem, t - C::EMAX + NS);
     const int kf = t - C::P.maxlag;
     if (kf >= K0 && kf < K1) {
         constexpr int sl = (U - C::P.maxlag) & M;
@@ -190,16 +199,22 @@ __device__ __forceinline__ void ana_step_slow(PairRing<Ana8Cfg<FV, FH>::RING, kW
 {
     using C = Ana8Cfg<FV, FH>;
     constexpr int RING = C::RING, M = RING - 1;
+    constexpr int EV0 = C::P.entry[0], EV1 = C::P.entry[1], NS = C::STAGES;
     int E0[kWideNP], O0[kWideNP], E1[kWideNP], O1[kWideNP];
-    ana_load_pair(X, smem, t, E0, O0, E1, O1);
+    ana_load_pair<NS, EV0, EV1>(X, smem, t, E0, O0, E1, O1);
     hlift8<FH, true, Ana8Ctx>(E0, O0, X);
     hlift8<FH, true, Ana8Ctx>(E1, O1, X);
-    const int ls = (t - ks) & M;
+    const int le = (t - EV0 - ks) & M, lo = (t - EV1 - ks) & M;
 #pragma unroll
-    for (int i = 0; i < RING; i++)
-        if (i == ls) ana_put<RING>(R, i, E0, O0, E1, O1);
+    for (int i = 0; i < RING; i++) {
+#pragma unroll
+        for (int q = 0; q < kWideNP; q++) {
+            if (i == le) { R.v[0][2 * q][i] = E0[q]; R.v[0][2 * q + 1][i] = O0[q]; }
+            if (i == lo) { R.v[1][2 * q][i] = E1[q]; R.v[1][2 * q + 1][i] = O1[q]; }
+        }
+    }
     vstep_slow<FV, RING, kWideNC, true>(R, t, ks, last);
-    ana_stage_pair(X, smem, t + kWideStages);
+    ana_stage_pair<NS>(X, smem, t - C::EMAX + NS);
     const int kf = t - C::P.maxlag;
     if (kf >= K0 && kf < K1) {
         const int sl = (kf - ks) & M;
@@ -221,7 +236,7 @@ dwt_stream8_kernel(AnaArgs A)
 {
     using C = Ana8Cfg<FV, FH, STEPS>;
     constexpr int NP = kWideNP, NC = kWideNC, RING = C::RING;
-    __shared__ __align__(16) WideVec smem[kWideStages * 4 * 32];
+    __shared__ __align__(16) WideVec smem[C::STAGES * 4 * 32];
     const int c = blockIdx.y;
     const int pic = blockIdx.z;
     const int tx = blockIdx.x % A.tiles_x[c];
@@ -261,7 +276,7 @@ dwt_stream8_kernel(AnaArgs A)
     const int K0 = ty * C::RSP, K1 = min(K0 + C::RSP, X.h2);
     const int ks = K0 - C::P.warm;
 #pragma unroll
-    for (int u = 0; u < kWideStages; u++) ana_stage_pair(X, smem, ks + u);
+    for (int u = 0; u < C::STAGES; u++) ana_stage_pair<C::STAGES>(X, smem, ks - C::EMAX + u);
     const int t_end = K1 - 1 + C::P.maxlag;
     for (int t0 = ks; t0 <= t_end; t0 += RING) {
         if (t0 >= C::P.back && t0 + RING - 1 <= last) {

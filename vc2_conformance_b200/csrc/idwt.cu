@@ -56,7 +56,7 @@ __device__ __forceinline__ void vstage(int (&a)[NR])
     constexpr bool kAdd = (TYPE == 1 || TYPE == 3);
 #pragma unroll
     for (int n = 0; n < NR / 2; n++) {
-        typename std::conditional<(S >= 8), long long, int>::type sum = 0;
+        typename std::conditional<(S >= kWideAccS), long long, int>::type sum = 0;
 #pragma unroll
         for (int i = D; i < L + D; i++) {
             int pos = kEven ? 2 * (n + i) - 1 : 2 * (n + i);
@@ -136,7 +136,7 @@ __device__ __forceinline__ void hstage(int &E, int &O, int lane, bool edge, int 
         if (lane < lane_lo) src = lo;
         if (lane > lane_hi) src = hi;
     }
-    typename std::conditional<(S >= 8), long long, int>::type sum = 0;
+    typename std::conditional<(S >= kWideAccS), long long, int>::type sum = 0;
 #pragma unroll
     for (int i = D; i < L + D; i++) {
         // even update reads odd sample index n+i-1; odd update reads even sample index n+i

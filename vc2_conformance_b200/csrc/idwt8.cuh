@@ -25,7 +25,10 @@ struct Strip8Cfg {
     static constexpr StreamPlan PH = make_stream_plan(FH);
     // raw pairs are staged in shared memory by cp.async, so the register ring only holds the live
     // window of the vertical lifting
-    static constexpr int RING = P.back + 1 <= 4 ? 4 : (P.back + 1 <= 8 ? 8 : 16);
+    // (each row parity enters the ring only when a stage first touches it: P.entry)
+    static constexpr int RING = P.window <= 4 ? 4 : (P.window <= 8 ? 8 : 16);
+    static constexpr int EMAX = P.entry[0] > P.entry[1] ? P.entry[0] : P.entry[1];
+    static constexpr int STAGES = 4 + EMAX;   // shared-memory slots: 4 pairs of look-ahead + late entries
     static constexpr int STEPS = STEPS_;                                       // steps per strip (multiple of RING)
     static constexpr int RSP = STEPS - P.warm - P.maxlag;                      // output row pairs per strip
     static constexpr int HLQ = (get_filter(FH).halo + 2 * NP - 1) / (2 * NP);   // halo lanes left / right
@@ -53,12 +56,13 @@ struct RawPair {
     int ll[kWideNP], b0[kWideNP], b1[kWideNP], b2[kWideNP];
 };
 
-// issue the asynchronous copy of pair m (one commit group per pair)
+// issue the asynchronous copy of pair m (one commit group per pair); NS = number of stage slots
+template <int NS>
 __device__ __forceinline__ void stage_pair8(const Strip8Ctx &X, WideVec *smem, int m)
 {
     const int sy = min(max(m, 0), X.h - 1);
     const int idx = sy * X.wq + X.jqc;
-    WideVec *st = smem + ((m & (kWideStages - 1)) * 4) * 32 + X.lane;
+    WideVec *st = smem + ((((m % NS) + NS) % NS) * 4) * 32 + X.lane;
     cp_async_vec(st, X.ll + idx);
     cp_async_vec(st + 32, X.b0 + idx);
     cp_async_vec(st + 64, X.b1 + idx);
@@ -66,15 +70,19 @@ __device__ __forceinline__ void stage_pair8(const Strip8Ctx &X, WideVec *smem, i
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-// pair m has landed once at most kWideStages-1 younger groups are still in flight
-__device__ __forceinline__ void load_pair8(const Strip8Ctx &X, const WideVec *smem, int m, RawPair &r)
+// At step t the even row of pair t - E0 and the odd row of pair t - E1 enter the register ring.
+// The youngest of them was issued 3 commit groups before the newest group in flight.
+template <int NS, int E0, int E1>
+__device__ __forceinline__ void load_pair8(const Strip8Ctx &X, const WideVec *smem, int t, RawPair &r)
 {
-    asm volatile("cp.async.wait_group %0;" ::"n"(kWideStages - 1) : "memory");
-    const WideVec *st = smem + ((m & (kWideStages - 1)) * 4) * 32 + X.lane;
-    vec_to_array(st[0], r.ll);
-    vec_to_array(st[32], r.b0);
-    vec_to_array(st[64], r.b1);
-    vec_to_array(st[96], r.b2);
+    asm volatile("cp.async.wait_group %0;" ::"n"(3) : "memory");
+    const int me = t - E0, mo = t - E1;
+    const WideVec *se = smem + ((((me % NS) + NS) % NS) * 4) * 32 + X.lane;
+    const WideVec *so = smem + ((((mo % NS) + NS) % NS) * 4) * 32 + X.lane;
+    vec_to_array(se[0], r.ll);
+    vec_to_array(se[32], r.b0);
+    vec_to_array(so[64], r.b1);
+    vec_to_array(so[96], r.b2);
 }
 
 // Pull rows that will be needed kWidePrefetchL2 steps from now into L2 (two row pairs per call):
@@ -95,15 +103,15 @@ __device__ __forceinline__ void prefetch_pairs_l2(const Strip8Ctx &X, int m)
 
 // LL/HL feed the even row (even/odd columns), LH/HH the odd row (vh_synthesis :164-169)
 template <int RING>
-__device__ __forceinline__ void put_pair8(PairRing<RING, kWideNC> &R, int slot, const RawPair &r)
+__device__ __forceinline__ void put_pair8(PairRing<RING, kWideNC> &R, int slot_even, int slot_odd, const RawPair &r)
 {
-    // `slot` must be a compile-time constant at every call site (the call is force-inlined)
+    // the slots must be compile-time constants at every call site (the call is force-inlined)
 #pragma unroll
     for (int q = 0; q < kWideNP; q++) {
-        R.v[0][2 * q][slot] = r.ll[q];
-        R.v[0][2 * q + 1][slot] = r.b0[q];
-        R.v[1][2 * q][slot] = r.b1[q];
-        R.v[1][2 * q + 1][slot] = r.b2[q];
+        R.v[0][2 * q][slot_even] = r.ll[q];
+        R.v[0][2 * q + 1][slot_even] = r.b0[q];
+        R.v[1][2 * q][slot_odd] = r.b1[q];
+        R.v[1][2 * q + 1][slot_odd] = r.b2[q];
     }
 }
 
@@ -155,13 +163,14 @@ __device__ __forceinline__ void strip8_step_fast(PairRing<Strip8Cfg<FV, FH>::RIN
 {
     using C = Strip8Cfg<FV, FH>;
     constexpr int RING = C::RING, M = RING - 1;
+    constexpr int E0 = C::P.entry[0], E1 = C::P.entry[1], NS = C::STAGES;
     {
         RawPair r;
-        load_pair8(X, smem, t, r);
-        put_pair8<RING>(R, U & M, r);
+        load_pair8<NS, E0, E1>(X, smem, t, r);
+        put_pair8<RING>(R, (U - E0) & M, (U - E1) & M, r);
     }
     vstep_fast<FV, U, RING, kWideNC>(R);
-    stage_pair8(X, smem, t + kWideStages);  // the slot of pair t is free again
+    stage_pair8<NS>(X, smem, t - C::EMAX + NS);  // the slot of pair t - EMAX is free again
     const int kf = t - C::P.maxlag;
     if (kf >= K0 && kf < K1) {
         constexpr int sl = (U - C::P.maxlag) & M;
@@ -189,14 +198,20 @@ __device__ __forceinline__ void strip8_step_slow(PairRing<Strip8Cfg<FV, FH>::RIN
 {
     using C = Strip8Cfg<FV, FH>;
     constexpr int RING = C::RING, M = RING - 1;
+    constexpr int E0 = C::P.entry[0], E1 = C::P.entry[1], NS = C::STAGES;
     RawPair r;
-    load_pair8(X, smem, t, r);
-    const int ls = (t - ks) & M;
+    load_pair8<NS, E0, E1>(X, smem, t, r);
+    const int le = (t - E0 - ks) & M, lo = (t - E1 - ks) & M;
 #pragma unroll
-    for (int i = 0; i < RING; i++)
-        if (i == ls) put_pair8<RING>(R, i, r);
+    for (int i = 0; i < RING; i++) {
+#pragma unroll
+        for (int q = 0; q < kWideNP; q++) {
+            if (i == le) { R.v[0][2 * q][i] = r.ll[q]; R.v[0][2 * q + 1][i] = r.b0[q]; }
+            if (i == lo) { R.v[1][2 * q][i] = r.b1[q]; R.v[1][2 * q + 1][i] = r.b2[q]; }
+        }
+    }
     vstep_slow<FV, RING, kWideNC>(R, t, ks, last);
-    stage_pair8(X, smem, t + kWideStages);
+    stage_pair8<NS>(X, smem, t - C::EMAX + NS);
     const int kf = t - C::P.maxlag;
     if (kf >= K0 && kf < K1) {
         const int sl = (kf - ks) & M;
@@ -227,7 +242,7 @@ __device__ __forceinline__ void run_strip8(const Strip8Ctx &X, WideVec *smem, in
     const int K0 = ty * C::RSP, K1 = min(K0 + C::RSP, X.h);
     const int ks = K0 - C::P.warm;
 #pragma unroll
-    for (int u = 0; u < kWideStages; u++) stage_pair8(X, smem, ks + u);
+    for (int u = 0; u < C::STAGES; u++) stage_pair8<C::STAGES>(X, smem, ks - C::EMAX + u);
     const int t_end = K1 - 1 + C::P.maxlag;
     for (int t0 = ks; t0 <= t_end; t0 += RING) {
         if (t0 >= C::P.back && t0 + RING - 1 <= last) {
@@ -245,7 +260,7 @@ idwt_stream8_kernel(LevelArgs A)
 {
     using C = Strip8Cfg<FV, FH, STEPS>;
     constexpr int NP = kWideNP, NC = kWideNC;
-    __shared__ __align__(16) WideVec smem[kWideStages * 4 * 32];
+    __shared__ __align__(16) WideVec smem[C::STAGES * 4 * 32];
     const int c = blockIdx.y;
     const int pic = blockIdx.z;
     const int tx = blockIdx.x % A.tiles_x[c];

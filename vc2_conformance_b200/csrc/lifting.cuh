@@ -14,6 +14,12 @@
 
 namespace vc2b {
 
+// Lifting sums accumulate in 32 bits except for stages with S >= kWideAccS (Fidelity, S = 8, eight
+// taps up to 161; Daubechies (9,7), S = 12, taps up to 6497), which accumulate in 64 bits.  The int32
+// envelope check (params.cu, pass_gain) bounds every 32-bit accumulator.  (With 32-bit sums Fidelity
+// runs 1.6x faster but a depth-4 Fidelity transform would only be safe for |coefficient| <= 533.)
+constexpr int kWideAccS = 8;
+
 struct StageDef {
     int type;  // 1 even += odd, 2 even -= odd, 3 odd += even, 4 odd -= even
     int S, L, D;
@@ -85,8 +91,8 @@ __device__ __forceinline__ void lift_stage(int32_t *__restrict__ tile, int tstri
         if (VERT) { n = item / other; o = item - n * other; }
         else { o = item / npairs; n = item - o * npairs; }
         const int gn = gn0 + n;
-        // S >= 8 filters (Fidelity, Daubechies) have large taps: accumulate in 64 bits
-        typename std::conditional<(S >= 8), long long, int>::type sum = 0;
+        // large-tap filters (Fidelity, Daubechies) accumulate in 64 bits
+        typename std::conditional<(S >= kWideAccS), long long, int>::type sum = 0;
 #pragma unroll
         for (int i = D; i < L + D; i++) {
             int pos;

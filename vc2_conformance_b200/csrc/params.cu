@@ -98,7 +98,7 @@ int make_dev_params(const vc2b_params *p, DevParams *d)
 
 // ---------------------------------------------------------------------------------------------
 // int32 envelope of the transforms.  The reference computes in unbounded integers; the kernels
-// hold samples in int32 (accumulating in int64 only for the S >= 8 filters).  These bounds
+// hold samples in int32 (accumulating in int64 only for the S >= 8 stages).  These bounds
 // propagate the largest possible magnitude through every level using the L-infinity operator
 // norms of the lifting passes and report the worst value that must fit 31 bits.
 // ---------------------------------------------------------------------------------------------
@@ -135,7 +135,7 @@ static PassGain pass_gain(int filter, bool analysis)
                 }
                 double accnorm = 0.0;
                 for (int c = 0; c < N; c++) accnorm += acc[c] < 0 ? -acc[c] : acc[c];
-                if (st.S < 8 && accnorm > g.worst) g.worst = accnorm;  // int32 accumulator
+                if (st.S < kWideAccS && accnorm > g.worst) g.worst = accnorm;  // int32 accumulator
                 const int t = even ? 2 * n : 2 * n + 1;
                 double rown = 0.0;
                 for (int c = 0; c < N; c++) {

@@ -21,6 +21,9 @@ struct StreamPlan {
     int lag[4];
     int maxlag;      // pair t - maxlag is final at the end of step t
     int back;        // oldest pair read at step t is t - back
+    int entry[2];    // row parity q of pair m is first touched at step m + entry[q]: it may enter the ring late
+    int backq[2];    // oldest pair of parity q still needed at step t is t - backq[q]
+    int window;      // ring slots needed when each parity enters at its entry lag
     int warm;        // pairs of warm-up before the first exact output
     int prefetch;    // raw pairs loaded ahead of the step that first needs them
     int ring;        // power of two >= back + 1 + prefetch
@@ -60,6 +63,19 @@ __host__ __device__ constexpr StreamPlan make_stream_plan(int filter, bool analy
     p.back = p.maxlag;
     for (int s = 0; s < p.ns; s++)
         if (p.lag[s] - p.dmin[s] > p.back) p.back = p.lag[s] - p.dmin[s];
+    p.entry[0] = p.entry[1] = 1 << 20;
+    p.backq[0] = p.backq[1] = p.maxlag;
+    for (int s = 0; s < p.ns; s++) {
+        const int w = p.parity[s], r = 1 - p.parity[s];
+        if (p.lag[s] < p.entry[w]) p.entry[w] = p.lag[s];
+        if (p.lag[s] - p.dmax[s] < p.entry[r]) p.entry[r] = p.lag[s] - p.dmax[s];
+        if (p.lag[s] - p.dmin[s] > p.backq[r]) p.backq[r] = p.lag[s] - p.dmin[s];
+    }
+    for (int q = 0; q < 2; q++)
+        if (p.entry[q] == (1 << 20) || p.entry[q] < 0) p.entry[q] = 0;
+    p.window = 1;
+    for (int q = 0; q < 2; q++)
+        if (p.backq[q] - p.entry[q] + 1 > p.window) p.window = p.backq[q] - p.entry[q] + 1;
     p.warm = (f.halo + 1) / 2;
     p.prefetch = 4;
     int r = 8;
@@ -120,7 +136,7 @@ __device__ __forceinline__ void vstage_fast(PairRing<RING, NC> &R)
     constexpr int par = P.parity[SIDX];
     constexpr int k = U - P.lag[SIDX];
     constexpr bool add = (st.type == 1 || st.type == 3);
-    using Acc = typename std::conditional<(st.S >= 8), long long, int>::type;
+    using Acc = typename std::conditional<(st.S >= kWideAccS), long long, int>::type;
 #pragma unroll
     for (int c = 0; c < NC; c++) {
         Acc sum = folded_taps<st.L, Acc>(st.taps, [&](int i) {
@@ -147,7 +163,7 @@ __device__ __forceinline__ void vstage_slow(PairRing<RING, NC> &R, int t, int ks
     if (k < 0 || k > last) return;
 #pragma unroll
     for (int c = 0; c < NC; c++) {
-        typename std::conditional<(st.S >= 8), long long, int>::type sum = 0;
+        typename std::conditional<(st.S >= kWideAccS), long long, int>::type sum = 0;
 #pragma unroll
         for (int i = 0; i < st.L; i++) {
             int m = k + P.dmin[SIDX] + i;

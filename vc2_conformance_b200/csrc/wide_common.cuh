@@ -23,9 +23,9 @@ __device__ __forceinline__ int4 array_to_vec(const int (&a)[4]) { return make_in
 __device__ __forceinline__ uint2 array_to_uvec(const uint32_t (&a)[2]) { return make_uint2(a[0], a[1]); }
 __device__ __forceinline__ uint4 array_to_uvec(const uint32_t (&a)[4]) { return make_uint4(a[0], a[1], a[2], a[3]); }
 
-// Shared-memory staging of raw row pairs: stage (m mod kWideStages) holds the four subband vectors
-// of pair m for every lane (lane-private slots, so no warp synchronisation is needed).
-constexpr int kWideStages = 4;
+// Shared-memory staging of raw row pairs: stage slot (m mod STAGES) holds the four vectors of pair m
+// for every lane (lane-private slots, so no warp synchronisation is needed); STAGES = 4 pairs of
+// look-ahead plus the largest entry lag of the vertical filter (stream_lift.cuh).
 
 __device__ __forceinline__ void cp_async_vec(WideVec *smem_dst, const WideVec *gsrc)
 {
@@ -48,7 +48,7 @@ __device__ __forceinline__ void hstage8(int (&E)[kWideNP], int (&O)[kWideNP], co
     constexpr int dmin = P.dmin[SIDX], dmax = P.dmax[SIDX];
     constexpr int NL = dmin < 0 ? -dmin : 0, NR = dmax > 0 ? dmax : 0;
     static_assert(NL <= NP && NR <= NP, "neighbour lanes only");
-    using Acc = typename std::conditional<(st.S >= 8), long long, int>::type;
+    using Acc = typename std::conditional<(st.S >= kWideAccS), long long, int>::type;
     int src[NP];
 #pragma unroll
     for (int i = 0; i < NP; i++) src[i] = even ? O[i] : E[i];
