@@ -217,3 +217,37 @@ def test_picture_encode_entry_point():
         assert (band.reshape(-1) == exp[: band.size]).all()
         last = np.array(st[key][p.dwt_depth]["HH"])
         assert (last.reshape(-1) == exp[off[-1]:]).all()
+
+
+@pytest.mark.parametrize("name", ["hq_lossy_legall_d3", "ld_lossy_haar_shift_d2"])
+def test_fragmented_picture_path(name):
+    """The calls fragment_parse makes (decoder/fragment_syntax.py:44-181): initialize_fragment_state,
+    then `slice` per slice in fragments of a few slices, dc_prediction after the last one, then
+    picture_decode at fragmented_picture_done (decoder/stream.py:130-133)."""
+    from vc2_conformance_b200 import pseudocode as P
+    from vc2_conformance_b200.params import params_from_arrays
+
+    z = load("pictures")
+    p = params_from_arrays(z[name + ".params"], z[name + ".quant_matrix"])
+    qm = _qm_dict(z[name + ".quant_matrix"], p.dwt_depth, p.dwt_depth_ho)
+    data = z[name + ".data"].tobytes()
+    st, f = _decoder_state(p, qm, data)
+    got = []
+    st["_output_picture_callback"] = lambda pic, vp, pcm: got.append(pic)
+    P.initialize_fragment_state(st)
+    ns = p.slices_x * p.slices_y
+    for n in range(ns):  # fragment_data's loop
+        sy, sx = divmod(n, p.slices_x)
+        P.fragment_slice(st, sx, sy)
+        st["fragment_slices_received"] += 1
+        st["_fragment_slices_remaining"] -= 1
+        if st["fragment_slices_received"] == ns:
+            st["fragmented_picture_done"] = True
+            if p.is_ld:
+                lvl0 = "LL" if p.dwt_depth_ho == 0 else "L"
+                for key in ("y_transform", "c1_transform", "c2_transform"):
+                    P.dc_prediction(st[key][0][lvl0])
+    assert st["current_byte"] == 0xAB and st["next_bit"] == 7
+    P.picture_decode(st)
+    for c, key in enumerate(["Y", "C1", "C2"]):
+        assert (np.array(got[0][key]) == z[name + ".decoded%d" % c]).all(), (name, key)

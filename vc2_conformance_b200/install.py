@@ -22,6 +22,10 @@ BINDINGS = [
     ("vc2_conformance.decoder.stream", "picture_decode", P.picture_decode),
     # decoder/picture_syntax.py:52,90: wavelet_transform -> transform_data(state)
     ("vc2_conformance.decoder.picture_syntax", "transform_data", P.transform_data),
+    # decoder/fragment_syntax.py:28-32,140,168,175-181: fragmented pictures buffer slice bytes
+    ("vc2_conformance.decoder.fragment_syntax", "initialize_fragment_state", P.initialize_fragment_state),
+    ("vc2_conformance.decoder.fragment_syntax", "slice", P.fragment_slice),
+    ("vc2_conformance.decoder.fragment_syntax", "dc_prediction", P.dc_prediction),
     # encoder/pictures.py:115,386: transform_and_slice_picture -> picture_encode(state, picture)
     ("vc2_conformance.encoder.pictures", "picture_encode", P.picture_encode),
     # the star namespace third parties use (pseudocode/__init__.py:96-107)

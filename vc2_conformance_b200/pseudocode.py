@@ -28,6 +28,7 @@ __all__ = [
     "remove_offset_picture", "remove_offset_component",
     "picture_decode", "picture_encode", "inverse_wavelet_transform", "forward_wavelet_transform",
     "dc_prediction", "apply_dc_prediction", "transform_data", "DeviceTransform",
+    "initialize_fragment_state", "fragment_slice",
 ]
 
 INT32_MAX = (1 << 31) - 1
@@ -263,7 +264,11 @@ def _dc(band, inverse):
 
 
 def dc_prediction(band):
-    """(13.4) In place."""
+    """(13.4) In place.  A band that comes from a :class:`DeviceTransform` of an LD picture has
+    already been predicted on the device (``vc2b_unpack`` applies it): calling this on it, as
+    ``fragment_data`` does after the last slice (decoder/fragment_syntax.py:171-181), is a no-op."""
+    if isinstance(band, _PredictedBand):
+        return
     _dc(band, False)
 
 
@@ -273,6 +278,10 @@ def apply_dc_prediction(band):
 
 
 # ---- whole pictures ----------------------------------------------------------------------------
+
+class _PredictedBand(list):
+    """Level-0 band of a DeviceTransform: DC prediction already applied on the device."""
+
 
 class DeviceTransform(dict):
     """``state["y_transform"]``-compatible container produced by :func:`transform_data`.  It keeps
@@ -291,7 +300,10 @@ class DeviceTransform(dict):
             self._filled = True
             g = self.codec.g
             flat = self.codec.coeff_components(0)[self.comp]
-            dict.update(self, _flat_to_coeff_dict(g, self.comp, flat))
+            d = _flat_to_coeff_dict(g, self.comp, flat)
+            for orient in list(d[0]):
+                d[0][orient] = _PredictedBand(d[0][orient])
+            dict.update(self, d)
 
     def __getitem__(self, k):
         self._fill()
@@ -451,3 +463,102 @@ def _reference_errors():
         "InvalidSliceYLength": InvalidSliceYLength,
         "UnexpectedEndOfStream": UnexpectedEndOfStream,
     }
+
+
+# ---- fragmented pictures (decoder/fragment_syntax.py:140-181) ------------------------------------------
+
+class _FragmentedTransform(DeviceTransform):
+    """``state["*_transform"]`` of a fragmented picture: slices are buffered as bytes and unpacked on
+    the device when the last one has arrived (or when somebody looks at the coefficients)."""
+
+    def __init__(self, shared, comp):
+        dict.__init__(self)
+        self.shared = shared
+        self.comp = comp
+        self._filled = False
+
+    @property
+    def codec(self):
+        return self.shared.finish()
+
+    @codec.setter
+    def codec(self, value):  # DeviceTransform.__init__ is bypassed; nothing to set
+        pass
+
+
+class _FragmentBuffer(object):
+    def __init__(self, p):
+        self.p = p
+        self.data = bytearray()
+        self._codec = None
+
+    def finish(self):
+        from .device import BatchCodec
+
+        if self._codec is None:
+            codec = BatchCodec(self.p, 1)
+            codec.decode_streams([bytes(self.data)], check=False)
+            st = codec.status_host(1)[0]
+            if st[0] == capi.ST_INT32_ENVELOPE:
+                raise EnvelopeError("picture leaves the int32 envelope")
+            if st[0] != capi.ST_OK:
+                raise ValueError("fragmented picture incomplete or corrupt (status %d at slice %d)" % (st[0], st[1]))
+            self._codec = codec
+        return self._codec
+
+
+def initialize_fragment_state(state):
+    """(14.3) decoder/fragment_syntax.py:140: coefficient containers that buffer slice bytes."""
+    shared = _FragmentBuffer(params_from_state(state))
+    state["y_transform"] = _FragmentedTransform(shared, 0)
+    state["c1_transform"] = _FragmentedTransform(shared, 1)
+    state["c2_transform"] = _FragmentedTransform(shared, 2)
+    state["fragment_slices_received"] = 0
+    state["_fragment_slices_remaining"] = state["slices_x"] * state["slices_y"]
+    state["fragmented_picture_done"] = False
+
+
+def _read_bytes(state, n):
+    """n whole bytes from the byte-aligned reader (decoder/io.py:152-206 semantics)."""
+    assert state["next_bit"] == 7, "slices of a fragment start byte aligned"
+    errors = _reference_errors()
+    out = bytearray()
+    if n == 0:
+        return out
+    if state["current_byte"] is None:
+        raise (errors["UnexpectedEndOfStream"]() if errors else EOFError("UnexpectedEndOfStream"))
+    out.append(state["current_byte"])
+    rest = state["_file"].read(n)  # n-1 more bytes of this slice + the next current byte
+    out += rest[: n - 1]
+    if len(rest) < n - 1:
+        state["current_byte"] = None
+        raise (errors["UnexpectedEndOfStream"]() if errors else EOFError("UnexpectedEndOfStream"))
+    state["current_byte"] = bytearray(rest)[n - 1] if len(rest) == n else None
+    return out
+
+
+def fragment_slice(state, sx, sy):
+    """Replacement for ``slice`` as called by fragment_data (decoder/fragment_syntax.py:168): consumes
+    exactly the bytes of slice (sx, sy) and buffers them; the device unpacks the whole picture once
+    every slice is there.  Per-slice level constraints are checked like hq_slice / ld_slice do."""
+    shared = state["y_transform"].shared
+    errors = _reference_errors()
+    if (state["parse_code"] & 0xF8) == 0xC8:  # is_ld
+        n = sy * state["slices_x"] + sx
+        nbytes = ((n + 1) * state["slice_bytes_numerator"]) // state["slice_bytes_denominator"] - (
+            n * state["slice_bytes_numerator"]) // state["slice_bytes_denominator"]
+        chunk = _read_bytes(state, nbytes)
+        if errors and nbytes:
+            errors["assert_level_constraint"](state, "qindex", chunk[0] >> 1)
+    else:
+        scaler = state["slice_size_scaler"]
+        chunk = _read_bytes(state, state["slice_prefix_bytes"] + 1)
+        if errors:
+            errors["assert_level_constraint"](state, "qindex", chunk[-1])
+        for _ in range(3):
+            length = _read_bytes(state, 1)
+            chunk += length
+            chunk += _read_bytes(state, scaler * length[0])
+        if errors:
+            errors["assert_level_constraint"](state, "total_slice_bytes", len(chunk))
+    shared.data += chunk
