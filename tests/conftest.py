@@ -11,6 +11,15 @@ for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+    # The CUDA library and the C oracle are built artefacts (git-ignored): build them if a fresh
+    # checkout is being tested.  nvcc cross-compiles without a GPU.
+    from vc2_conformance_b200 import _build
+
+    if not os.path.exists(_build.LIB):
+        _build.build()
+    import oracle
+
+    oracle.build()
 
 
 def pytest_collection_modifyitems(config, items):
