@@ -260,6 +260,11 @@ __device__ __forceinline__ long long hq_total_length(const DevParams &P, const F
     return ((n + 1) * F.total_coeff_bytes) / den - (n * F.total_coeff_bytes) / den;
 }
 
+// last qindex found for a picture (search hint shared by the warps of that picture; stale or racy
+// values only cost probes)
+constexpr int kHintSlots = 1024;
+__device__ int g_qindex_hint[kHintSlots];
+
 __global__ void __launch_bounds__(kQWarps * 32)
 quantize_fit_kernel(DevParams P, FitArgs F, const int32_t *__restrict__ coeffs, int npictures,
                     int32_t *__restrict__ qindex_out, int32_t *__restrict__ bits_out)
@@ -326,10 +331,28 @@ quantize_fit_kernel(DevParams P, FitArgs F, const int32_t *__restrict__ coeffs, 
     if (target < 0) {
         lo = hi;  // cannot fit: reported as the saturated index (the reference would not terminate)
     } else {
+        // Neighbouring slices of a picture usually need almost the same index: gallop outwards from
+        // the last answer any warp published for this picture (a hint only -- every bound used
+        // below is established by an actual probe), then bisect the bracket.
+        const int hint = g_qindex_hint[pic & (kHintSlots - 1)];
+        if (hint > lo && hint < hi) {
+            if (fits(hint)) {
+                hi = hint;
+                for (int step = 1; hi - step > lo; step *= 2) {
+                    if (fits(hi - step)) hi -= step; else { lo = hi - step + 1; break; }
+                }
+            } else {
+                lo = hint + 1;
+                for (int step = 1; lo + step < hi; step *= 2) {
+                    if (!fits(lo + step - 1)) lo += step; else { hi = lo + step - 1; break; }
+                }
+            }
+        }
         while (lo < hi) {
             const int mid = (lo + hi) >> 1;
             if (fits(mid)) hi = mid; else lo = mid + 1;
         }
+        if (lane == 0) g_qindex_hint[pic & (kHintSlots - 1)] = lo;
     }
     fits(lo);
     if (lane == 0) {
