@@ -50,6 +50,12 @@ WORKLOADS = {
         params=dict(luma_width=1920, luma_height=1080, color_diff_width=960, color_diff_height=1080,
                     luma_depth=10, wavelet_index=1, dwt_depth=3, slices_x=60, slices_y=135),
         pictures=120, bits_per_sample=2.5),
+    # BASELINE.json configs[0] read literally: 8 x 8 slices (uneven: 135/8 rows), 31980 + 2*15990 coefficients each
+    "cfg1_8x8": dict(
+        name="1920x1080 10-bit 4:2:2 HQ, LeGall(5,3) depth 3, 8x8 slices (uneven), 120-picture sequence",
+        params=dict(luma_width=1920, luma_height=1080, color_diff_width=960, color_diff_height=1080,
+                    luma_depth=10, wavelet_index=1, dwt_depth=3, slices_x=8, slices_y=8),
+        pictures=120, bits_per_sample=2.5),
     "cfg3": dict(
         name="1920x1080 interlaced LD (1920x540 fields) 10-bit 4:2:2, Haar-with-shift depth 2, 60x135 slices, 4:1",
         params=dict(luma_width=1920, luma_height=540, color_diff_width=960, color_diff_height=540,
@@ -472,7 +478,7 @@ def run_ours(args):
                    "kernels": "hq_walk_kernel + unpack_hq_kernel" if not p.is_ld else "unpack_ld_kernel + dc_prediction_kernel"},
         "idwt": {"ms_per_step": ms_idwt, "achieved": idwt_gbs, "frac": idwt_gbs / peak,
                  "algorithmic_bytes_per_picture": idwt_bytes // NP,
-                 "kernels": "idwt_level_kernel x %d levels (last fused with crop+clip+offset)"
+                 "kernels": "idwt_stream8_kernel x %d levels (last fused with crop+clip+offset)"
                             % (p.dwt_depth + p.dwt_depth_ho)},
     }
     dom = "unpack" if ms_unpack >= ms_idwt else "idwt"

@@ -7,17 +7,18 @@
 //
 // Design (B200): the stage is HBM-bound only if the lifting itself is nearly free, so the
 // lifting lives entirely in REGISTERS.  One launch per transform level covers all three
-// components and a group of pictures.  A WARP owns a tile of the level's output: lane l holds
-// the column pair (2j, 2j+1), j = j0 + l, for R + 2*halo rows, loaded straight from the four
-// subbands with coalesced 128-byte row reads (vh_synthesis interleave, :164-169).  Columns are
-// lifted with wavelet_index inside each thread (static register indices after unrolling); rows
-// are lifted with wavelet_index_ho by exchanging neighbours with warp shuffles (:172-175).  Halo
-// rows / lanes are recomputed by neighbouring tiles instead of being exchanged.  No shared
-// memory, no block-level barrier.  The edge clamps of lift1-4 (:210-212, :240-242) are
-// reproduced by refreshing out-of-range rows/lanes from the boundary sample of the same parity
-// before every stage -- only in tiles that touch an edge.  The last level applies the rounding
+// components and a group of pictures.  A WARP owns a strip of the level's output and walks down
+// it one row pair per step: columns are lifted with wavelet_index by the streaming scheme of
+// stream_lift.cuh (static register slots after unrolling), rows with wavelet_index_ho by
+// exchanging neighbours with warp shuffles (:172-175).  Halo rows / lanes are recomputed by
+// neighbouring strips instead of being exchanged; no block-level barrier.  The edge clamps of
+// lift1-4 (:210-212, :240-242) are reproduced by clamped (dynamic-slot) steps at the top / bottom
+// of the picture and by refreshing out-of-range lanes from the boundary lane before every
+// horizontal stage -- only in strips that touch an edge.  The last level applies the rounding
 // shift (:177-182, shift from wavelet_index_ho :198-201), crops (:282), clips (:327), offsets
-// (:301) and stores packed uint16 pairs.
+// (:301) and stores packed uint16.  Kernels: idwt_stream8_kernel (idwt8.cuh: 8 columns per lane,
+// cp.async staging; the fast path), idwt_stream_kernel (2 columns per lane; any width / filter
+// pair), idwt_rows_kernel (horizontal-only levels).
 #include "stream_lift.cuh"
 
 namespace vc2b {
@@ -42,83 +43,6 @@ struct LevelArgs {
     int32_t tiles_x[3], tiles_y[3];
     int32_t ncomp;
 };
-
-// ---- register-resident vertical lifting -----------------------------------------------------
-
-// One lifting stage down a column held in registers a[0..NR) (window row i = global row ys + i,
-// ys even).  Sources are clamped to the window: rows nearer than `halo` to a window edge that
-// is not a picture edge come out wrong and are never consumed.
-template <int TYPE, int S, int L, int D, int T0, int T1, int T2, int T3, int T4, int T5, int T6, int T7, int NR>
-__device__ __forceinline__ void vstage(int (&a)[NR])
-{
-    constexpr int taps[8] = {T0, T1, T2, T3, T4, T5, T6, T7};
-    constexpr bool kEven = (TYPE == 1 || TYPE == 2);
-    constexpr bool kAdd = (TYPE == 1 || TYPE == 3);
-#pragma unroll
-    for (int n = 0; n < NR / 2; n++) {
-        typename std::conditional<(S >= kWideAccS), long long, int>::type sum = 0;
-#pragma unroll
-        for (int i = D; i < L + D; i++) {
-            int pos = kEven ? 2 * (n + i) - 1 : 2 * (n + i);
-            pos = pos < 0 ? (kEven ? 1 : 0) : pos;
-            pos = pos > NR - 1 ? (kEven ? NR - 1 : NR - 2) : pos;
-            sum += (decltype(sum))taps[i - D] * a[pos];
-        }
-        if (S > 0) sum += (decltype(sum))1 << (S > 0 ? S - 1 : 0);
-        sum >>= S;
-        if (kAdd) a[kEven ? 2 * n : 2 * n + 1] += (int)sum;
-        else a[kEven ? 2 * n : 2 * n + 1] -= (int)sum;
-    }
-}
-
-// lift1-4 clamp their source positions to the array (picture_decoding.py:210-212, :240-242):
-// a source row outside the picture reads the nearest in-range row of the same parity, with the
-// value it has when the stage runs.  PAR = parity of the rows the coming stage READS.
-// top: window rows [0, kt) lie above the picture (kt = 0 unless the tile is on the top edge);
-// kb: first window row below the picture (>= NR when the tile does not reach the bottom).
-template <int PAR, int NR>
-__device__ __forceinline__ void vrefresh(int (&a)[NR], int kt, int kb)
-{
-    if (kt > 0) {
-        int bv = 0;
-#pragma unroll
-        for (int i = 0; i < NR; i++)
-            if ((i & 1) == PAR && i == kt + PAR) bv = a[i];
-#pragma unroll
-        for (int i = 0; i < NR; i++)
-            if ((i & 1) == PAR && i < kt) a[i] = bv;
-    }
-    if (kb < NR) {
-        int bv = 0;
-#pragma unroll
-        for (int i = 0; i < NR; i++)
-            if ((i & 1) == PAR && i == kb - 2 + PAR) bv = a[i];
-#pragma unroll
-        for (int i = 0; i < NR; i++)
-            if ((i & 1) == PAR && i >= kb) a[i] = bv;
-    }
-}
-
-template <int F, int SIDX, int NR>
-__device__ __forceinline__ void vrun_stage(int (&a)[NR], bool edge, int kt, int kb)
-{
-    constexpr FilterDef f = get_filter(F);
-    constexpr StageDef s = f.st[SIDX];
-    constexpr bool kEven = (s.type == 1 || s.type == 2);
-    if (edge) vrefresh<kEven ? 1 : 0, NR>(a, kt, kb);
-    vstage<s.type, s.S, s.L, s.D, s.taps[0], s.taps[1], s.taps[2], s.taps[3], s.taps[4], s.taps[5], s.taps[6],
-           s.taps[7], NR>(a);
-}
-
-template <int F, int NR>
-__device__ __forceinline__ void vlift(int (&a)[NR], bool edge, int kt, int kb)
-{
-    constexpr int ns = get_filter(F).nstages;
-    vrun_stage<F, 0, NR>(a, edge, kt, kb);
-    if constexpr (ns > 1) vrun_stage<F, (ns > 1 ? 1 : 0), NR>(a, edge, kt, kb);
-    if constexpr (ns > 2) vrun_stage<F, (ns > 2 ? 2 : 0), NR>(a, edge, kt, kb);
-    if constexpr (ns > 3) vrun_stage<F, (ns > 3 ? 3 : 0), NR>(a, edge, kt, kb);
-}
 
 // ---- horizontal lifting across lanes ---------------------------------------------------------
 
@@ -169,23 +93,21 @@ __device__ __forceinline__ void hlift(int &E, int &O, int lane, bool edge, int l
     if constexpr (ns > 3) hrun_stage<F, (ns > 3 ? 3 : 0)>(E, O, lane, edge, lane_lo, lane_hi);
 }
 
-// ---- the level kernel -------------------------------------------------------------------------
+// ---- horizontal-only level kernel (h_synthesis, picture_decoding.py:134) --------------------------
 
-template <int FV, int FH, bool VERT>
-struct TileCfg {
-    static constexpr int HV = VERT ? get_filter(FV).halo : 0;  // halo rows above / below
-    static constexpr int HL = get_filter(FH).halo / 2;         // halo lanes left / right
-    static constexpr int R = VERT ? (HV >= 8 ? 16 : 32) : 16;  // output rows per warp tile
-    static constexpr int NR = R + 2 * HV;                      // rows held per thread
-    static constexpr int WOUT = 2 * (32 - 2 * HL);             // output columns per warp tile
+template <int FH>
+struct RowCfg {
+    static constexpr int HL = get_filter(FH).halo / 2;  // halo lanes left / right
+    static constexpr int R = 16;                         // rows per warp tile
+    static constexpr int WOUT = 2 * (32 - 2 * HL);       // output columns per warp tile
 };
 
-template <int FV, int FH, bool VERT>
+template <int FH>
 __global__ void __launch_bounds__(kIdwtWarps * 32)
-idwt_level_kernel(LevelArgs A)
+idwt_rows_kernel(LevelArgs A)
 {
-    using C = TileCfg<FV, FH, VERT>;
-    constexpr int HV = C::HV, HL = C::HL, R = C::R, NR = C::NR, WOUT = C::WOUT;
+    using C = RowCfg<FH>;
+    constexpr int HL = C::HL, R = C::R, WOUT = C::WOUT;
 
     const int lane = threadIdx.x & 31;
     const int c = blockIdx.y;
@@ -196,7 +118,7 @@ idwt_level_kernel(LevelArgs A)
     if (ty >= A.tiles_y[c]) return;
 
     const int w = A.w[c], h = A.h[c];
-    const int W2 = 2 * w, H2 = VERT ? 2 * h : h;
+    const int W2 = 2 * w;
     const int X0 = tx * WOUT, Y0 = ty * R;
     const int j = (X0 >> 1) - HL + lane;          // column pair owned by this lane
     const int jc = min(max(j, 0), w - 1);
@@ -206,74 +128,33 @@ idwt_level_kernel(LevelArgs A)
 
     const int32_t *ll = A.ll[c] + (long long)pic * A.ll_pic_stride[c];
     const int32_t *b0 = A.hb[c][0] + (long long)pic * A.hb_pic_stride;
-
-    int e[NR], o[NR];  // columns 2j and 2j+1, window rows [0, NR) = global rows ys + i
-    const int ys = Y0 - HV;
-    if (VERT) {
-        const int32_t *b1 = A.hb[c][1] + (long long)pic * A.hb_pic_stride;
-        const int32_t *b2 = A.hb[c][2] + (long long)pic * A.hb_pic_stride;
-        const int sy0 = ys >> 1;  // ys even (may be negative)
-#pragma unroll
-        for (int i = 0; i < NR / 2; i++) {
-            const int sy = min(max(sy0 + i, 0), h - 1);
-            const long long g = (long long)sy * w + jc;
-            e[2 * i] = __ldg(ll + g);
-            o[2 * i] = __ldg(b0 + g);
-            e[2 * i + 1] = __ldg(b1 + g);
-            o[2 * i + 1] = __ldg(b2 + g);
-        }
-        const int kt = ys < 0 ? -ys : 0;
-        const int kb = H2 - ys;
-        const bool vedge = (kt > 0) || (kb < NR);
-        vlift<FV, NR>(e, vedge, kt, kb);
-        vlift<FV, NR>(o, vedge, kt, kb);
-    } else {
-#pragma unroll
-        for (int i = 0; i < NR; i++) {
-            const int sy = min(Y0 + i, h - 1);
-            const long long g = (long long)sy * w + jc;
-            e[i] = __ldg(ll + g);
-            o[i] = __ldg(b0 + g);
-        }
-    }
-
-    // rows of the tile: horizontal lifting, rounding shift, store
     const int shift = A.shift;
     const int rnd = shift > 0 ? (1 << (shift - 1)) : 0;
     const bool lane_ok = (lane >= HL) && (lane < 32 - HL) && (j >= 0) && (j < w);
-    if (A.final_u16) {
-        const int cw = A.crop_w[c], ch = A.crop_h[c];
-        const int half = 1 << (A.depth[c] - 1);
-        uint16_t *dst = A.pic[c] + (long long)pic * A.pic_pic_stride;
-#pragma unroll
-        for (int i = 0; i < R; i++) {
-            const int gy = Y0 + i;
-            int E = e[HV + i], O = o[HV + i];
-            hlift<FH>(E, O, lane, hedge, lane_lo, lane_hi);
-            if (lane_ok && gy < ch) {
+    const int cw = A.crop_w[c], ch = A.crop_h[c];
+    const int half = 1 << (A.depth[c] - 1);
+    uint16_t *pdst = A.final_u16 ? A.pic[c] + (long long)pic * A.pic_pic_stride : nullptr;
+    int32_t *idst = A.final_u16 ? nullptr : A.out[c] + (long long)pic * A.out_pic_stride[c];
+#pragma unroll 4
+    for (int i = 0; i < R; i++) {
+        const int gy = Y0 + i;
+        const int sy = min(gy, h - 1);
+        const long long g = (long long)sy * w + jc;
+        int E = __ldg(ll + g), O = __ldg(b0 + g);   // L -> even column, H -> odd column (:140-143)
+        hlift<FH>(E, O, lane, hedge, lane_lo, lane_hi);
+        if (!lane_ok || gy >= h) continue;
+        if (A.final_u16) {
+            if (gy < ch) {
                 int v0 = (E + rnd) >> shift, v1 = (O + rnd) >> shift;
                 v0 = min(max(v0, -half), half - 1) + half;
                 v1 = min(max(v1, -half), half - 1) + half;
                 const long long idx = (long long)gy * cw + 2 * j;
-                if (2 * j + 1 < cw && !(reinterpret_cast<uintptr_t>(dst + idx) & 3)) {
-                    *reinterpret_cast<uint32_t *>(dst + idx) = (uint32_t)v0 | ((uint32_t)v1 << 16);
-                } else {
-                    if (2 * j < cw) dst[idx] = (uint16_t)v0;
-                    if (2 * j + 1 < cw) dst[idx + 1] = (uint16_t)v1;
-                }
+                if (2 * j < cw) pdst[idx] = (uint16_t)v0;
+                if (2 * j + 1 < cw) pdst[idx + 1] = (uint16_t)v1;
             }
-        }
-    } else {
-        int32_t *dst = A.out[c] + (long long)pic * A.out_pic_stride[c];
-#pragma unroll
-        for (int i = 0; i < R; i++) {
-            const int gy = Y0 + i;
-            int E = e[HV + i], O = o[HV + i];
-            hlift<FH>(E, O, lane, hedge, lane_lo, lane_hi);
-            if (lane_ok && gy < H2) {
-                int2 v = make_int2((E + rnd) >> shift, (O + rnd) >> shift);
-                *reinterpret_cast<int2 *>(dst + (long long)gy * W2 + 2 * j) = v;
-            }
+        } else {
+            *reinterpret_cast<int2 *>(idst + (long long)gy * W2 + 2 * j) =
+                make_int2((E + rnd) >> shift, (O + rnd) >> shift);
         }
     }
 }
@@ -499,14 +380,14 @@ static int launch_level_t(const LevelArgs &A_in, int npic, cudaStream_t s)
         dim3 grid(maxtiles, A.ncomp, npic);
         idwt_stream_kernel<FV, FH><<<grid, 32, 0, s>>>(A);
     } else {
-        using C = TileCfg<FV, FH, false>;
+        using C = RowCfg<FH>;
         for (int c = 0; c < A.ncomp; c++) {
             A.tiles_x[c] = (2 * A.w[c] + C::WOUT - 1) / C::WOUT;
             A.tiles_y[c] = (A.h[c] + C::R - 1) / C::R;
             maxtiles = max(maxtiles, A.tiles_x[c] * A.tiles_y[c]);
         }
         dim3 grid((maxtiles + kIdwtWarps - 1) / kIdwtWarps, A.ncomp, npic);
-        idwt_level_kernel<FV, FH, false><<<grid, kIdwtWarps * 32, 0, s>>>(A);
+        idwt_rows_kernel<FH><<<grid, kIdwtWarps * 32, 0, s>>>(A);
     }
     VC2B_CHECK_LAUNCH();
     return 0;
