@@ -18,6 +18,9 @@
 // fetched words, so dangling values come out exactly as in the reference.
 // Consecutive lanes hold consecutive coefficients, so the scatter into the
 // subband rectangles is coalesced per rectangle row.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace vc2b {
@@ -709,6 +712,12 @@ unpack_ld_kernel(DevParams P, const uint8_t *__restrict__ data, const int64_t *_
     }
 }
 
+}  // namespace vc2b
+
+#include "unpack_lanes.cuh"
+
+namespace vc2b {
+
 // ---------------------------------------------------------------------------
 // DC prediction (decoder/transform_data_syntax.py:63 dc_prediction and its inverse
 // encoder/pictures.py:202 apply_dc_prediction).  One CTA per (picture, component); thread y
@@ -852,26 +861,49 @@ int vc2b_unpack(const vc2b_params *p, const uint8_t *d_data, const int64_t *d_pi
     if (st) return st;
     if (npictures <= 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
-    const long long warps = (long long)npictures * P.slices_x * P.slices_y;
-    // persistent warps, each walking a run of consecutive slices (about 16 CTAs per SM worth of
-    // work items keeps the tail short)
-    const long long max_blocks = 148LL * 64;
-    long long nblk = (warps + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    if (nblk > max_blocks) nblk = max_blocks;
-    const unsigned blocks = (unsigned)nblk;
+    if (!P.is_ld && !d_slice_offset) return VC2B_E_BAD_PARAMS;
+    // Small slices (the production geometry): one LANE per slice.  Large slices: one WARP per slice.
+    // VC2B_UNPACK=warp|lanes overrides the choice (tests exercise both kernels on the same streams).
+    bool lanes = lanes_eligible(P);
+    if (const char *force = getenv("VC2B_UNPACK")) {
+        if (!strcmp(force, "warp")) lanes = false;
+        if (!strcmp(force, "lanes") && !lanes) return VC2B_E_UNSUPPORTED;
+    }
     if (P.is_ld) {
         ld_init_status_kernel<<<(npictures + 127) / 128, 128, 0, s>>>(P, d_pic_offset, npictures, d_status);
         VC2B_CHECK_LAUNCH();
-        unpack_ld_kernel<<<blocks, kWarpsPerBlock * 32, 0, s>>>(P, d_data, d_pic_offset, npictures, d_coeffs,
-                                                                d_qindex, d_status);
-        VC2B_CHECK_LAUNCH();
-        // using_dc_prediction (pseudocode/parse_code_functions.py:70): LD pictures only
-        dc_prediction_kernel<<<npictures * 3, kDcThreads, 0, s>>>(P, d_coeffs, 0, d_status);
+    }
+    if (lanes) {
+        const long long tasks = (long long)npictures * ((P.slices_x * P.slices_y + 31) / 32);
+        long long nblk = (tasks + kLaneWarps - 1) / kLaneWarps;
+        const long long max_blocks = 148LL * 5;  // persistent: 5 CTAs per SM are resident (41 KB shared each)
+        if (nblk > max_blocks) nblk = max_blocks;
+        if (P.is_ld)
+            unpack_lanes_kernel<true><<<(unsigned)nblk, kLaneWarps * 32, 0, s>>>(P, d_data, d_pic_offset, npictures,
+                                                                                 nullptr, d_coeffs, d_qindex, d_status);
+        else
+            unpack_lanes_kernel<false><<<(unsigned)nblk, kLaneWarps * 32, 0, s>>>(
+                P, d_data, d_pic_offset, npictures, d_slice_offset, d_coeffs, d_qindex, d_status);
         VC2B_CHECK_LAUNCH();
     } else {
-        if (!d_slice_offset) return VC2B_E_BAD_PARAMS;
-        unpack_hq_kernel<<<blocks, kWarpsPerBlock * 32, 0, s>>>(P, d_data, d_pic_offset, npictures,
-                                                                d_slice_offset, d_coeffs, d_qindex, d_status);
+        const long long warps = (long long)npictures * P.slices_x * P.slices_y;
+        // persistent warps, each walking a run of consecutive slices (about 16 CTAs per SM worth of
+        // work items keeps the tail short)
+        const long long max_blocks = 148LL * 64;
+        long long nblk = (warps + kWarpsPerBlock - 1) / kWarpsPerBlock;
+        if (nblk > max_blocks) nblk = max_blocks;
+        const unsigned blocks = (unsigned)nblk;
+        if (P.is_ld)
+            unpack_ld_kernel<<<blocks, kWarpsPerBlock * 32, 0, s>>>(P, d_data, d_pic_offset, npictures, d_coeffs,
+                                                                    d_qindex, d_status);
+        else
+            unpack_hq_kernel<<<blocks, kWarpsPerBlock * 32, 0, s>>>(P, d_data, d_pic_offset, npictures,
+                                                                    d_slice_offset, d_coeffs, d_qindex, d_status);
+        VC2B_CHECK_LAUNCH();
+    }
+    if (P.is_ld) {
+        // using_dc_prediction (pseudocode/parse_code_functions.py:70): LD pictures only
+        dc_prediction_kernel<<<npictures * 3, kDcThreads, 0, s>>>(P, d_coeffs, 0, d_status);
         VC2B_CHECK_LAUNCH();
     }
     long long safe = idwt_max_safe_coeff(p);

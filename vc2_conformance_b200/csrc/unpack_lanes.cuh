@@ -1,0 +1,520 @@
+// unpack_lanes.cuh -- lane-per-slice coefficient unpacking (included by unpack.cu).
+//
+// Same job as the warp-per-slice kernels of unpack.cu (hq_slice / ld_slice / slice_band /
+// color_diff_slice_band / read_sintb / inverse_quant, decoder/transform_data_syntax.py:145-335,
+// decoder/io.py:246-313, pseudocode/quantization.py:18), for the production-style geometry of many
+// SMALL slices (<= kLaneMaxCoef coefficients per slice component).
+//
+// Design (B200): exp-Golomb decoding is a dependent chain per bounded block, but the blocks of
+// different slices are independent, so here every LANE owns a slice and walks its own bit string:
+// a 64-bit bit buffer in registers, an 8-bit window LUT that yields length, magnitude and sign of
+// every code of up to 8 bits in one shared-memory lookup, refills predicated every fourth
+// coefficient.  A warp therefore decodes 32 slices in lockstep at ~1 instruction per coefficient
+// and lane instead of the ~4 warp instructions per coefficient of the scan-based warp-per-slice
+// scheme.  The dequantised values go through a padded 32x33 shared-memory tile (written
+// [coefficient][slice], read [slice][coefficient], both conflict-free) so that the stores to the
+// subband rectangles are issued per slice with consecutive lanes on consecutive coefficients --
+// the same coalescing as the warp-per-slice kernel, and every coefficient is written exactly once
+// (no zero-fill pass).  The coefficient -> (band, y, x) map is built once per CTA for the dimensions
+// of slice (0, 0); slices of ragged geometries whose rectangles differ take a slower path that
+// locates each coefficient from the slice's own band table.
+#pragma once
+
+namespace vc2b {
+
+constexpr int kLaneWarps = 4;            // warps per CTA
+constexpr int kLaneBands = 16;           // subbands per component this kernel supports
+constexpr int kLaneMaxCoef = 512;        // coefficients per slice component this kernel supports
+constexpr int kLaneBaseStride = kLaneBands + 1;
+
+struct LaneWarp {                        // per-warp shared memory
+    int32_t tile[32 * 33];               // [coefficient of the chunk][slice], row stride 33
+    int32_t base[32 * kLaneBaseStride];  // [slice][band]: offset of the rectangle in the component
+    uint32_t cntw[kLaneBands][32];       // [band][slice]: coefficients | width << 16
+};
+
+struct LaneBlock {                       // per-CTA shared memory
+    uint32_t map[2][kLaneMaxCoef];       // [luma, chroma]: coefficient -> band << 26 | y * stride + x
+    int32_t ref_w[2][kLaneBands];        // rectangle of slice (0, 0): floor(band / slices)
+    int32_t ref_h[2][kLaneBands];
+    int32_t even_x[2][kLaneBands];       // ref_w if the band divides evenly between the slices, else -1
+    int32_t even_y[2][kLaneBands];
+    int32_t ref_ncoef[2];
+    uint16_t slut[256];                  // 8-bit window -> length | negative << 7 | magnitude << 8
+    uint2 qtab[kQTab];
+};
+
+// Codes that fit an 8-bit window, sign included: 0 -> "1"; +-1..2 -> 4 bits; +-3..6 -> 6 bits;
+// +-7..14 -> 8 bits (decoder/io.py:285-313).  Length 0 marks a longer code.
+__device__ __forceinline__ void build_lane_lut(uint16_t *slut, int tid, int nthreads)
+{
+    for (int e = tid; e < 256; e += nthreads) {
+        int value = 1, pos = 7;
+        uint32_t entry = 0;
+        bool done = false;
+        while (pos >= 0) {
+            const int follow = (e >> pos) & 1;
+            pos--;
+            if (follow) { done = true; break; }
+            if (pos < 0) break;
+            value = (value << 1) | ((e >> pos) & 1);
+            pos--;
+        }
+        if (done) {
+            value -= 1;
+            if (value == 0) entry = 1;
+            else if (pos >= 0) entry = (uint32_t)(8 - pos) | ((uint32_t)value << 8) | (((e >> pos) & 1) << 7);
+        }
+        slut[e] = (uint16_t)entry;
+    }
+}
+
+struct LaneReader {
+    const uint32_t *wp;   // next word to load
+    uint64_t buf;         // bit buffer, next bit at the top; bits below `avail` are zero
+    uint32_t ahead;       // the word after the buffer, loaded one refill early (hides the load latency)
+    int avail;            // valid bits in buf
+    int remaining;        // bits of the bounded block at and after *wp (<= 0: past its end)
+};
+
+// The next 32 bits of the bounded block; ones past its end (decoder/io.py:246-252).
+__device__ __forceinline__ uint32_t lane_next_word(LaneReader &R)
+{
+    uint32_t w = 0xffffffffu;
+    if (R.remaining > 0) {
+        w = __byte_perm(__ldg(R.wp), 0, 0x0123);
+        if (R.remaining < 32) w |= 0xffffffffu >> R.remaining;
+    }
+    R.wp++;
+    R.remaining -= 32;
+    return w;
+}
+
+__device__ __forceinline__ void lane_refill(LaneReader &R)
+{
+    if (R.avail <= 32) {
+        R.buf |= ((uint64_t)R.ahead << 32) >> R.avail;
+        R.avail += 32;
+        R.ahead = lane_next_word(R);
+    }
+}
+
+__device__ __forceinline__ void lane_reader_init(LaneReader &R, const uint8_t *blk, int bit_off, long long nbits,
+                                                 bool active)
+{
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(blk);
+    R.wp = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
+    const int skip = (int)(addr & 3) * 8 + bit_off;   // <= 31
+    long long rem = nbits + skip;
+    if (rem > (1LL << 30)) rem = 1LL << 30;           // a slice of this kernel never reads that far
+    R.remaining = active ? (int)rem : 0;
+    const uint32_t w0 = lane_next_word(R);
+    const uint32_t w1 = lane_next_word(R);
+    R.ahead = lane_next_word(R);
+    R.buf = (((uint64_t)w0 << 32) | w1) << skip;
+    R.avail = 64 - skip;
+}
+
+// A lane whose block left the int32 envelope stops parsing: it reads zeros from here on.
+__device__ __forceinline__ void lane_reader_kill(LaneReader &R)
+{
+    R.buf = ~0ull;
+    R.ahead = 0xffffffffu;
+    R.avail = 64;
+    R.remaining = 0;
+}
+
+// The tail of read_sintb (decoder/io.py:302) for a code longer than the 8-bit window.
+// Restores avail >= 32.  Returns false when the value has 32 or more data bits.
+__device__ __forceinline__ bool lane_read_long(LaneReader &R, uint32_t &mag, uint32_t &neg)
+{
+    if (R.avail < 32) lane_refill(R);   // the short-path schedule only guarantees 8 bits
+    const uint32_t h2 = (uint32_t)(R.buf >> 32);
+    const uint32_t f = h2 & 0xAAAAAAAAu;
+    bool ok = true;
+    if (f) {  // at most 15 data bits: the whole code sits in 32 bits
+        const int k = __clz(f) >> 1;
+        uint32_t v = h2 >> (32 - 2 * k);
+        v = (v | (v >> 1)) & 0x33333333u;
+        v = (v | (v >> 2)) & 0x0f0f0f0fu;
+        v = (v | (v >> 4)) & 0x00ff00ffu;
+        v = (v | (v >> 8)) & 0x0000ffffu;
+        mag = ((1u << k) | v) - 1u;
+        neg = (h2 >> (30 - 2 * k)) & 1;
+        R.buf <<= (2 * k + 2);
+        R.avail -= 2 * k + 2;
+    } else {  // 16 or more data bits: bit-serial
+        uint32_t value = 1;
+        int nd = 0;
+        while (true) {
+            const uint32_t top2 = (uint32_t)(R.buf >> 62);
+            if (top2 & 2) break;
+            if (nd >= 31) {  // a 32nd data bit: outside the int32 envelope
+                ok = false;
+                break;
+            }
+            value = (value << 1) | (top2 & 1);
+            nd++;
+            R.buf <<= 2;
+            R.avail -= 2;
+            if (R.avail < 32) lane_refill(R);
+        }
+        mag = value - 1u;
+        neg = (uint32_t)(R.buf >> 62) & 1;
+        R.buf <<= 2;
+        R.avail -= 2;
+    }
+    if (R.avail < 32) lane_refill(R);
+    return ok;
+}
+
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr)
+{
+    uint16_t v;
+    asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return v;
+}
+
+// Decodes one bounded block per lane (component `comp` of the lane's slice) and scatters the
+// dequantised coefficients.  INTERLEAVED: values alternate C1, C2 (color_diff_slice_band,
+// decoder/transform_data_syntax.py:315); `out2` is then the C2 base.
+template <bool INTERLEAVED>
+__device__ __forceinline__ void lanes_block(const DevParams &P, const int comp, LaneWarp &W, const LaneBlock &S,
+                                            const bool active, const int sx, const int sy, const int qindex,
+                                            const uint8_t *blk, const int bit_off, const long long nbits,
+                                            int32_t *__restrict__ out, int32_t *__restrict__ out2, const int lane,
+                                            uint32_t &maxabs, bool &ovf)
+{
+    constexpr int I = INTERLEAVED ? 1 : 0;
+    const int mc = comp ? 1 : 0;
+    const int nb = P.nb;
+
+    // ---- the slice's rectangles (slice_left/right/top/bottom, pseudocode/slice_sizes.py:108-127)
+    int ncoef = 0;
+    bool match = true;
+    __syncwarp();
+    for (int b = 0; b < nb; b++) {
+        const Band &B = P.band[comp][b];
+        // lanes without a slice run along on the reference rectangle and decode zeros
+        int w = S.ref_w[mc][b], h = S.ref_h[mc][b], base = 0;
+        if (active) {
+            int x1, x2, y1, y2;
+            const int ex = S.even_x[mc][b], ey = S.even_y[mc][b];
+            if (ex >= 0) {
+                x1 = ex * sx;
+                x2 = x1 + ex;
+            } else if ((unsigned)B.w < 32768u && P.slices_x < 65536) {
+                x1 = (int)(((unsigned)B.w * (unsigned)sx) / (unsigned)P.slices_x);
+                x2 = (int)(((unsigned)B.w * (unsigned)(sx + 1)) / (unsigned)P.slices_x);
+            } else {
+                x1 = (int)(((long long)B.w * sx) / P.slices_x);
+                x2 = (int)(((long long)B.w * (sx + 1)) / P.slices_x);
+            }
+            if (ey >= 0) {
+                y1 = ey * sy;
+                y2 = y1 + ey;
+            } else if ((unsigned)B.h < 32768u && P.slices_y < 65536) {
+                y1 = (int)(((unsigned)B.h * (unsigned)sy) / (unsigned)P.slices_y);
+                y2 = (int)(((unsigned)B.h * (unsigned)(sy + 1)) / (unsigned)P.slices_y);
+            } else {
+                y1 = (int)(((long long)B.h * sy) / P.slices_y);
+                y2 = (int)(((long long)B.h * (sy + 1)) / P.slices_y);
+            }
+            w = x2 - x1;
+            h = y2 - y1;
+            base = B.off + y1 * B.w + x1;
+            match = match && (w == S.ref_w[mc][b]) && (h == S.ref_h[mc][b]);
+        }
+        W.base[lane * kLaneBaseStride + b] = base;
+        W.cntw[b][lane] = (uint32_t)(w * h) | ((uint32_t)w << 16);
+        ncoef += w * h;
+    }
+    const int ncodes = ncoef << I;
+    int jmax = ncodes;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) jmax = max(jmax, __shfl_xor_sync(0xffffffffu, jmax, d));
+    const uint32_t act_mask = __ballot_sync(0xffffffffu, active);
+    const uint32_t match_mask = __ballot_sync(0xffffffffu, active && match);
+    __syncwarp();
+    if (act_mask == 0) return;
+    const bool uniform = match_mask == act_mask;  // every lane decodes the reference rectangle
+
+    LaneReader R;
+    lane_reader_init(R, blk, bit_off, nbits, active);
+
+    int b = -1, next = 0;
+    uint32_t qf = 0, qo = 0, satmask = 0;
+    const int refcodes = min(S.ref_ncoef[mc], kLaneMaxCoef) << I;
+    uint32_t slut_addr = (uint32_t)__cvta_generic_to_shared(S.slut);
+    asm volatile("" : "+r"(slut_addr));  // keep the address in a register (not rebuilt at every use)
+    int32_t *tile = &W.tile[lane];
+
+    // one code: read_sintb + inverse_quant, value to tile row i
+#define VC2B_LANE_STEP(i)                                                                            \
+    {                                                                                                \
+        if (j0 + (i) == next) {  /* next band (slice_quantizers, transform_data_syntax.py:255) */    \
+            do {                                                                                     \
+                b++;                                                                                 \
+                next += (int)(W.cntw[b][lane] & 0xffffu) << I;                                       \
+            } while (j0 + (i) == next);                                                              \
+            const int q = max(qindex - P.band[comp][b].qm, 0);                                       \
+            const uint2 qq = S.qtab[min(q, kQTab - 1)];                                              \
+            qf = qq.x;                                                                               \
+            qo = qq.y;                                                                               \
+            satmask = qf == 0xffffffffu ? 0xffffffffu : 0u;                                          \
+        }                                                                                            \
+        const uint32_t hi = (uint32_t)(R.buf >> 32);                                                 \
+        const uint32_t e = lds_u16(slut_addr + 2 * (hi >> 24));                                      \
+        const int len = e & 15;                                                                      \
+        uint32_t mag = e >> 8, neg = e & 0x80;                                                       \
+        if (len == 0) {                                                                              \
+            if (!lane_read_long(R, mag, neg)) {                                                      \
+                bad |= 1u;                                                                           \
+                lane_reader_kill(R);                                                                 \
+            }                                                                                        \
+        } else {                                                                                     \
+            R.buf <<= len;                                                                           \
+            R.avail -= len;                                                                          \
+        }                                                                                            \
+        /* inverse_quant (pseudocode/quantization.py:18): (m*qf + qo + 2) // 4 */                    \
+        const unsigned long long t64 = (unsigned long long)mag * qf + qo;                            \
+        uint32_t t = (uint32_t)(t64 >> 2);                                                           \
+        if (mag == 0) t = 0;                                                                         \
+        hiacc |= (uint32_t)(t64 >> 32);                                                              \
+        bad |= mag & satmask;                                                                        \
+        maxabs = max(maxabs, t);                                                                     \
+        tile[(i) * 33] = neg ? -(int32_t)t : (int32_t)t;                                             \
+    }
+
+    // the int32 envelope was left if some m*qf+qo reached 2^33 (hiacc >= 2), a non-zero value met a
+    // saturated quantiser or a value had 32 or more data bits (bad != 0)
+    uint32_t hiacc = 0, bad = 0;
+    for (int j0 = 0; j0 < jmax; j0 += 32) {
+        // ---- decode: lane = slice, 32 codes each --------------------------------------------------
+        if (uniform && j0 + 32 <= refcodes) {
+#pragma unroll 1
+            for (int g = 0; g < 8; g++) {
+                VC2B_LANE_STEP(0)
+                VC2B_LANE_STEP(1)
+                VC2B_LANE_STEP(2)
+                VC2B_LANE_STEP(3)
+                lane_refill(R);
+                j0 += 4;
+                tile += 4 * 33;
+            }
+            j0 -= 32;
+            tile -= 32 * 33;
+        } else {
+#pragma unroll 1
+            for (int i = 0; i < 32; i++) {
+                if (j0 < ncodes) VC2B_LANE_STEP(0)
+                if (R.avail < 32) lane_refill(R);
+                j0 += 1;
+                tile += 33;
+            }
+            j0 -= 32;
+            tile -= 32 * 33;
+        }
+        __syncwarp();
+
+        // ---- store: per slice, lane = coefficient --------------------------------------------------
+        const int j = j0 + lane;
+        const int jj = j >> I;
+        const uint32_t loc = j < refcodes ? S.map[mc][jj] : 0u;
+        const int mb = loc >> 26, moff = loc & 0x3ffffffu;
+        int32_t *dst = (INTERLEAVED && (j & 1)) ? out2 : out;
+        if (uniform) {
+            if (j < refcodes) {
+                int32_t *p = dst + moff;
+                const int32_t *tb = &W.tile[lane * 33];
+                const int32_t *bb = &W.base[mb];
+                if (act_mask == 0xffffffffu) {
+#pragma unroll
+                    for (int s = 0; s < 32; s++) p[bb[s * kLaneBaseStride]] = tb[s];
+                } else {
+#pragma unroll 4
+                    for (int s = 0; s < 32; s++)
+                        if ((act_mask >> s) & 1) p[bb[s * kLaneBaseStride]] = tb[s];
+                }
+            }
+        } else {
+            for (int s = 0; s < 32; s++) {
+                if (!((act_mask >> s) & 1)) continue;
+                if ((match_mask >> s) & 1) {
+                    if (j < refcodes) dst[W.base[s * kLaneBaseStride + mb] + moff] = W.tile[lane * 33 + s];
+                } else {
+                    const int ncodes_s = __shfl_sync(0xffffffffu, ncodes, s);
+                    if (j < ncodes_s) {
+                        int bb = 0, cum = 0;
+                        uint32_t cw = W.cntw[0][s];
+                        while (jj >= cum + (int)(cw & 0xffffu)) {
+                            cum += (int)(cw & 0xffffu);
+                            bb++;
+                            cw = W.cntw[bb][s];
+                        }
+                        const int local = jj - cum;
+                        const int w = (int)(cw >> 16);
+                        const int y = local / w;
+                        const int x = local - y * w;
+                        dst[W.base[s * kLaneBaseStride + bb] + y * P.band[comp][bb].w + x] = W.tile[lane * 33 + s];
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+#undef VC2B_LANE_STEP
+    if ((hiacc >> 1) != 0 || bad != 0) ovf = true;
+}
+
+__device__ __forceinline__ void build_lane_block(const DevParams &P, LaneBlock &S, int tid, int nthreads)
+{
+    build_lane_lut(S.slut, tid, nthreads);
+    build_qtab(S.qtab, tid, nthreads);
+    for (int idx = tid; idx < 2 * kLaneBands; idx += nthreads) {
+        const int mc = idx / kLaneBands, b = idx - mc * kLaneBands;
+        int rw = 0, rh = 0, ex = -1, ey = -1;
+        if (b < P.nb) {
+            const Band &B = P.band[mc][b];
+            rw = B.w / P.slices_x;
+            rh = B.h / P.slices_y;
+            if (rw * P.slices_x == B.w) ex = rw;
+            if (rh * P.slices_y == B.h) ey = rh;
+        }
+        S.ref_w[mc][b] = rw;
+        S.ref_h[mc][b] = rh;
+        S.even_x[mc][b] = ex;
+        S.even_y[mc][b] = ey;
+    }
+    __syncthreads();
+    if (tid < 2) {
+        int n = 0;
+        for (int b = 0; b < P.nb; b++) n += S.ref_w[tid][b] * S.ref_h[tid][b];
+        S.ref_ncoef[tid] = n;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < 2 * kLaneMaxCoef; idx += nthreads) {
+        const int mc = idx / kLaneMaxCoef, j = idx - mc * kLaneMaxCoef;
+        uint32_t loc = 0;
+        if (j < S.ref_ncoef[mc]) {
+            int b = 0, cum = 0;
+            while (j >= cum + S.ref_w[mc][b] * S.ref_h[mc][b]) {
+                cum += S.ref_w[mc][b] * S.ref_h[mc][b];
+                b++;
+            }
+            const int local = j - cum;
+            const int y = local / S.ref_w[mc][b];
+            const int x = local - y * S.ref_w[mc][b];
+            loc = ((uint32_t)b << 26) | (uint32_t)(y * P.band[mc][b].w + x);
+        }
+        S.map[mc][j] = loc;
+    }
+    __syncthreads();
+}
+
+// One LANE per slice; a warp task is 32 consecutive slices of one picture.
+template <bool LD>
+__global__ void __launch_bounds__(kLaneWarps * 32)
+unpack_lanes_kernel(DevParams P, const uint8_t *__restrict__ data, const int64_t *__restrict__ pic_offset,
+                    int npictures, const uint32_t *__restrict__ slice_offset, int32_t *__restrict__ coeffs,
+                    int32_t *__restrict__ qindex_out, int32_t *__restrict__ status)
+{
+    __shared__ LaneBlock S;
+    __shared__ LaneWarp Ws[kLaneWarps];
+    build_lane_block(P, S, threadIdx.x, blockDim.x);
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    LaneWarp &W = Ws[warp];
+    const int nslices = P.slices_x * P.slices_y;
+    const int tasks_per_pic = (nslices + 31) >> 5;
+    const long long total_tasks = (long long)npictures * tasks_per_pic;
+    for (long long t = (long long)blockIdx.x * kLaneWarps + warp; t < total_tasks;
+         t += (long long)gridDim.x * kLaneWarps) {
+        const int pic = (int)(t / tasks_per_pic);
+        const int n = (int)(t - (long long)pic * tasks_per_pic) * 32 + lane;
+        bool active = n < nslices;
+        const int sy = n / P.slices_x, sx = n - sy * P.slices_x;
+        const long long gw = (long long)pic * nslices + n;
+        const uint8_t *base = data + pic_offset[pic];
+        int32_t *pc = coeffs + (size_t)pic * P.pic_coeffs;
+        uint32_t maxabs = 0;
+        bool ovf = false;
+
+        if (!LD) {
+            // hq_slice (decoder/transform_data_syntax.py:212)
+            const uint32_t off = active ? slice_offset[gw] : 0xffffffffu;
+            active = active && off != 0xffffffffu;  // at or after the slice where the stream ended
+            long long pos = (long long)off + P.slice_prefix_bytes;
+            const int qindex = active ? (int)__ldg(base + pos) : 0;
+            pos += 1;
+            if (qindex_out && active) qindex_out[gw] = qindex;
+#pragma unroll 1
+            for (int c = 0; c < 3; c++) {
+                const long long length = active ? (long long)P.slice_size_scaler * __ldg(base + pos) : 0;
+                pos += 1;
+                lanes_block<false>(P, c, W, S, active, sx, sy, qindex, base + pos, 0, 8 * length, pc + P.comp_off[c],
+                                   nullptr, lane, maxabs, ovf);
+                pos += length;
+            }
+        } else {
+            // ld_slice (decoder/transform_data_syntax.py:145)
+            const long long nbytes = pic_offset[pic + 1] - pic_offset[pic];
+            long long s0 = 0, s1 = 0;
+            if (active) {
+                s0 = ld_slice_offset(P, n);
+                s1 = ld_slice_offset(P, n + 1);
+                if (s1 > nbytes) active = false;  // stream ended inside this slice (ld_init_status_kernel)
+            }
+            int qindex = 0, length_bits = 0;
+            long long slice_y_length = 0, bits_left = 0;
+            if (active) {
+                const long long sbytes = s1 - s0;
+                // 7-bit qindex, then intlog2(8*slice_bytes-7)-bit slice_y_length (decoder/io.py:230)
+                length_bits = ilog2_ceil(8 * sbytes - 7);
+                long long hdr = 0;
+                const int hbytes = (7 + length_bits + 7) >> 3;
+                for (int i = 0; i < hbytes; i++) hdr = (hdr << 8) | __ldg(base + s0 + i);
+                hdr >>= (8 * hbytes - 7 - length_bits);
+                qindex = (int)(hdr >> length_bits);
+                slice_y_length = hdr & ((1LL << length_bits) - 1);
+                bits_left = 8 * sbytes - 7 - length_bits;
+                if (qindex_out) qindex_out[gw] = qindex;
+                if (slice_y_length > bits_left) {  // InvalidSliceYLength, transform_data_syntax.py:166
+                    report(status, pic, n, VC2B_ST_INVALID_SLICE_Y_LENGTH);
+                    active = false;
+                }
+            }
+            const long long ybit = s0 * 8 + 7 + length_bits;
+            lanes_block<false>(P, 0, W, S, active, sx, sy, qindex, base + (ybit >> 3), (int)(ybit & 7), slice_y_length,
+                               pc + P.comp_off[0], nullptr, lane, maxabs, ovf);
+            const long long cbit = ybit + slice_y_length;
+            lanes_block<true>(P, 1, W, S, active, sx, sy, qindex, base + (cbit >> 3), (int)(cbit & 7),
+                              bits_left - slice_y_length, pc + P.comp_off[1], pc + P.comp_off[2], lane, maxabs, ovf);
+        }
+        ovf = __any_sync(0xffffffffu, ovf);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) maxabs = max(maxabs, __shfl_xor_sync(0xffffffffu, maxabs, d));
+        if (lane == 0 && (maxabs || ovf))
+            atomicMax(&status[4 * pic + 3], (ovf || maxabs > 0x7fffffffu) ? 0x7fffffff : (int)maxabs);
+    }
+}
+
+// Whether every slice component fits the lane-per-slice kernel.
+static bool lanes_eligible(const DevParams &P)
+{
+    if (P.nb > kLaneBands) return false;
+    for (int c = 0; c < 3; c++) {
+        long long tot = 0;
+        for (int b = 0; b < P.nb; b++) {
+            const long long cw = (P.band[c][b].w + P.slices_x - 1) / P.slices_x;
+            const long long ch = (P.band[c][b].h + P.slices_y - 1) / P.slices_y;
+            if (cw > 0xffff) return false;
+            tot += cw * ch;
+            if (tot > kLaneMaxCoef) return false;
+        }
+    }
+    return true;
+}
+
+}  // namespace vc2b
