@@ -72,30 +72,35 @@ __device__ __forceinline__ void build_lane_lut(uint16_t *slut, int tid, int nthr
 struct LaneReader {
     const uint32_t *wp;   // next word to load
     uint64_t buf;         // bit buffer, next bit at the top; bits below `avail` are zero
-    uint32_t ahead;       // the word after the buffer, loaded one refill early (hides the load latency)
+    uint32_t ahead;       // the word after the buffer as loaded (raw), fetched one refill early so
+                          // that the load latency is hidden; it is only looked at by the next refill
     int avail;            // valid bits in buf
     int remaining;        // bits of the bounded block at and after *wp (<= 0: past its end)
 };
 
-// The next 32 bits of the bounded block; ones past its end (decoder/io.py:246-252).
-__device__ __forceinline__ uint32_t lane_next_word(LaneReader &R)
+// Issues the load of the next word of the block (nothing is loaded past its end).
+__device__ __forceinline__ void lane_fetch(LaneReader &R)
 {
-    uint32_t w = 0xffffffffu;
-    if (R.remaining > 0) {
-        w = __byte_perm(__ldg(R.wp), 0, 0x0123);
-        if (R.remaining < 32) w |= 0xffffffffu >> R.remaining;
-    }
+    if (R.remaining > 0) R.ahead = __ldg(R.wp);
     R.wp++;
     R.remaining -= 32;
+}
+
+// The word fetched last as 32 bits of the bounded block: ones past its end (decoder/io.py:246-252).
+__device__ __forceinline__ uint32_t lane_ahead_bits(const LaneReader &R)
+{
+    const int rem = R.remaining + 32;   // bits of the block at and after the fetched word
+    uint32_t w = __byte_perm(R.ahead, 0, 0x0123);
+    if (rem < 32) w |= 0xffffffffu >> max(rem, 0);
     return w;
 }
 
 __device__ __forceinline__ void lane_refill(LaneReader &R)
 {
     if (R.avail <= 32) {
-        R.buf |= ((uint64_t)R.ahead << 32) >> R.avail;
+        R.buf |= ((uint64_t)lane_ahead_bits(R) << 32) >> R.avail;
         R.avail += 32;
-        R.ahead = lane_next_word(R);
+        lane_fetch(R);
     }
 }
 
@@ -108,9 +113,12 @@ __device__ __forceinline__ void lane_reader_init(LaneReader &R, const uint8_t *b
     long long rem = nbits + skip;
     if (rem > (1LL << 30)) rem = 1LL << 30;           // a slice of this kernel never reads that far
     R.remaining = active ? (int)rem : 0;
-    const uint32_t w0 = lane_next_word(R);
-    const uint32_t w1 = lane_next_word(R);
-    R.ahead = lane_next_word(R);
+    R.ahead = 0;
+    lane_fetch(R);
+    const uint32_t w0 = lane_ahead_bits(R);
+    lane_fetch(R);
+    const uint32_t w1 = lane_ahead_bits(R);
+    lane_fetch(R);
     R.buf = (((uint64_t)w0 << 32) | w1) << skip;
     R.avail = 64 - skip;
 }
@@ -119,9 +127,8 @@ __device__ __forceinline__ void lane_reader_init(LaneReader &R, const uint8_t *b
 __device__ __forceinline__ void lane_reader_kill(LaneReader &R)
 {
     R.buf = ~0ull;
-    R.ahead = 0xffffffffu;
     R.avail = 64;
-    R.remaining = 0;
+    R.remaining = -32;
 }
 
 // The tail of read_sintb (decoder/io.py:302) for a code longer than the 8-bit window.
@@ -166,6 +173,22 @@ __device__ __forceinline__ bool lane_read_long(LaneReader &R, uint32_t &mag, uin
     }
     if (R.avail < 32) lane_refill(R);
     return ok;
+}
+
+// Out-of-line copy for the hot loop: long codes are rare, and inlining them four times per loop
+// body spreads the hot instructions over several KB of code (instruction-fetch stalls).
+struct LaneLong {
+    LaneReader R;
+    uint32_t mag, neg;
+    int ok;
+};
+
+__device__ __noinline__ LaneLong lane_read_long_cold(LaneReader R)
+{
+    LaneLong o;
+    o.ok = lane_read_long(R, o.mag, o.neg) ? 1 : 0;
+    o.R = R;
+    return o;
 }
 
 __device__ __forceinline__ uint32_t lds_u16(uint32_t addr)
@@ -243,16 +266,29 @@ __device__ __forceinline__ void lanes_block(const DevParams &P, const int comp, 
     lane_reader_init(R, blk, bit_off, nbits, active);
 
     int b = -1, next = 0;
-    uint32_t qf = 0, qo = 0, satmask = 0;
+    uint32_t qf = 0, qo = 0, maxmag = 0;
     const int refcodes = min(S.ref_ncoef[mc], kLaneMaxCoef) << I;
     uint32_t slut_addr = (uint32_t)__cvta_generic_to_shared(S.slut);
     asm volatile("" : "+r"(slut_addr));  // keep the address in a register (not rebuilt at every use)
     int32_t *tile = &W.tile[lane];
 
+    // Largest magnitude read in the current band: inverse_quant is monotone in the magnitude, so the
+    // envelope bookkeeping (largest |coefficient|, overflow of m*qf+qo, saturated quantiser) is done
+    // once per band instead of once per coefficient.
+#define VC2B_LANE_CLOSE_BAND()                                                                       \
+    if (maxmag) {                                                                                    \
+        const unsigned long long tm = (unsigned long long)maxmag * qf + qo;                          \
+        maxabs = max(maxabs, (uint32_t)(tm >> 2));                                                   \
+        hiacc |= (uint32_t)(tm >> 32);                                                               \
+        if (qf == 0xffffffffu) bad |= 2u;                                                            \
+        maxmag = 0;                                                                                  \
+    }
+
     // one code: read_sintb + inverse_quant, value to tile row i
 #define VC2B_LANE_STEP(i)                                                                            \
     {                                                                                                \
         if (j0 + (i) == next) {  /* next band (slice_quantizers, transform_data_syntax.py:255) */    \
+            VC2B_LANE_CLOSE_BAND()                                                                   \
             do {                                                                                     \
                 b++;                                                                                 \
                 next += (int)(W.cntw[b][lane] & 0xffffu) << I;                                       \
@@ -261,14 +297,17 @@ __device__ __forceinline__ void lanes_block(const DevParams &P, const int comp, 
             const uint2 qq = S.qtab[min(q, kQTab - 1)];                                              \
             qf = qq.x;                                                                               \
             qo = qq.y;                                                                               \
-            satmask = qf == 0xffffffffu ? 0xffffffffu : 0u;                                          \
         }                                                                                            \
         const uint32_t hi = (uint32_t)(R.buf >> 32);                                                 \
-        const uint32_t e = lds_u16(slut_addr + 2 * (hi >> 24));                                      \
+        const uint32_t e = lds_u16(slut_addr + 2 * __byte_perm(hi, 0, 0x4443));                     \
         const int len = e & 15;                                                                      \
         uint32_t mag = e >> 8, neg = e & 0x80;                                                       \
-        if (len == 0) {                                                                              \
-            if (!lane_read_long(R, mag, neg)) {                                                      \
+        if (__builtin_expect(len == 0, 0)) {                                                         \
+            const LaneLong o = lane_read_long_cold(R);                                               \
+            R = o.R;                                                                                 \
+            mag = o.mag;                                                                             \
+            neg = o.neg;                                                                             \
+            if (!o.ok) {                                                                             \
                 bad |= 1u;                                                                           \
                 lane_reader_kill(R);                                                                 \
             }                                                                                        \
@@ -276,13 +315,10 @@ __device__ __forceinline__ void lanes_block(const DevParams &P, const int comp, 
             R.buf <<= len;                                                                           \
             R.avail -= len;                                                                          \
         }                                                                                            \
-        /* inverse_quant (pseudocode/quantization.py:18): (m*qf + qo + 2) // 4 */                    \
-        const unsigned long long t64 = (unsigned long long)mag * qf + qo;                            \
-        uint32_t t = (uint32_t)(t64 >> 2);                                                           \
-        if (mag == 0) t = 0;                                                                         \
-        hiacc |= (uint32_t)(t64 >> 32);                                                              \
-        bad |= mag & satmask;                                                                        \
-        maxabs = max(maxabs, t);                                                                     \
+        /* inverse_quant (pseudocode/quantization.py:18): (m*qf + qo + 2) // 4, zero stays zero */   \
+        const uint32_t qoe = mag ? qo : 0u;                                                          \
+        const uint32_t t = (uint32_t)(((unsigned long long)mag * qf + qoe) >> 2);                    \
+        maxmag = max(maxmag, mag);                                                                   \
         tile[(i) * 33] = neg ? -(int32_t)t : (int32_t)t;                                             \
     }
 
@@ -363,7 +399,9 @@ __device__ __forceinline__ void lanes_block(const DevParams &P, const int comp, 
         }
         __syncwarp();
     }
+    VC2B_LANE_CLOSE_BAND()
 #undef VC2B_LANE_STEP
+#undef VC2B_LANE_CLOSE_BAND
     if ((hiacc >> 1) != 0 || bad != 0) ovf = true;
 }
 
