@@ -11,9 +11,9 @@
 // every code of up to 8 bits in one shared-memory lookup, refills predicated every fourth
 // coefficient.  A warp therefore decodes 32 slices in lockstep at ~1 instruction per coefficient
 // and lane instead of the ~4 warp instructions per coefficient of the scan-based warp-per-slice
-// scheme.  The dequantised values go through a padded 32x33 shared-memory tile (written
+// scheme.  The dequantised values go through a padded 16x34 shared-memory tile (written
 // [coefficient][slice], read [slice][coefficient], both conflict-free) so that the stores to the
-// subband rectangles are issued per slice with consecutive lanes on consecutive coefficients --
+// subband rectangles are issued per slice pair with consecutive lanes on consecutive coefficients --
 // the same coalescing as the warp-per-slice kernel, and every coefficient is written exactly once
 // (no zero-fill pass).  The coefficient -> (band, y, x) map is built once per CTA for the dimensions
 // of slice (0, 0); slices of ragged geometries whose rectangles differ take a slower path that
@@ -26,9 +26,11 @@ constexpr int kLaneWarps = 4;            // warps per CTA
 constexpr int kLaneBands = 16;           // subbands per component this kernel supports
 constexpr int kLaneMaxCoef = 512;        // coefficients per slice component this kernel supports
 constexpr int kLaneBaseStride = kLaneBands + 1;
+constexpr int kLaneChunk = 16;           // codes per lane between two store phases
+constexpr int kLaneTS = 34;              // tile row stride: conflict-free for both access patterns
 
 struct LaneWarp {                        // per-warp shared memory
-    int32_t tile[32 * 33];               // [coefficient of the chunk][slice], row stride 33
+    int32_t tile[kLaneChunk * kLaneTS];  // [code of the chunk][slice]
     int32_t base[32 * kLaneBaseStride];  // [slice][band]: offset of the rectangle in the component
     uint32_t cntw[kLaneBands][32];       // [band][slice]: coefficients | width << 16
 };
@@ -285,9 +287,9 @@ __device__ __forceinline__ void lanes_block(const DevParams &P, const int comp, 
     }
 
     // one code: read_sintb + inverse_quant, value to tile row i
-#define VC2B_LANE_STEP(i)                                                                            \
+#define VC2B_LANE_STEP(i, CHK)                                                                       \
     {                                                                                                \
-        if (j0 + (i) == next) {  /* next band (slice_quantizers, transform_data_syntax.py:255) */    \
+        if (CHK && j0 + (i) == next) {  /* next band (slice_quantizers, transform_data_syntax.py:255) */ \
             VC2B_LANE_CLOSE_BAND()                                                                   \
             do {                                                                                     \
                 b++;                                                                                 \
@@ -319,42 +321,48 @@ __device__ __forceinline__ void lanes_block(const DevParams &P, const int comp, 
         const uint32_t qoe = mag ? qo : 0u;                                                          \
         const uint32_t t = (uint32_t)(((unsigned long long)mag * qf + qoe) >> 2);                    \
         maxmag = max(maxmag, mag);                                                                   \
-        tile[(i) * 33] = neg ? -(int32_t)t : (int32_t)t;                                             \
+        tile[(i) * kLaneTS] = neg ? -(int32_t)t : (int32_t)t;                                        \
     }
 
     // the int32 envelope was left if some m*qf+qo reached 2^33 (hiacc >= 2), a non-zero value met a
     // saturated quantiser or a value had 32 or more data bits (bad != 0)
     uint32_t hiacc = 0, bad = 0;
-    for (int j0 = 0; j0 < jmax; j0 += 32) {
-        // ---- decode: lane = slice, 32 codes each --------------------------------------------------
-        if (uniform && j0 + 32 <= refcodes) {
+    const int c = lane & 15, h = lane >> 4;   // store phase: half-warp h takes slice 2k+h, lane c its code c
+    for (int j0 = 0; j0 < jmax; j0 += kLaneChunk) {
+        // ---- decode: lane = slice, kLaneChunk codes each -------------------------------------------
+        if (uniform && j0 + kLaneChunk <= refcodes) {
 #pragma unroll 1
-            for (int g = 0; g < 8; g++) {
-                VC2B_LANE_STEP(0)
-                VC2B_LANE_STEP(1)
-                VC2B_LANE_STEP(2)
-                VC2B_LANE_STEP(3)
+            for (int g = 0; g < kLaneChunk / 4; g++) {
+                if (next - j0 >= 4) {  // no band starts within these four codes
+                    VC2B_LANE_STEP(0, false)
+                    VC2B_LANE_STEP(1, false)
+                    VC2B_LANE_STEP(2, false)
+                    VC2B_LANE_STEP(3, false)
+                } else {
+                    VC2B_LANE_STEP(0, true)
+                    VC2B_LANE_STEP(1, true)
+                    VC2B_LANE_STEP(2, true)
+                    VC2B_LANE_STEP(3, true)
+                }
                 lane_refill(R);
                 j0 += 4;
-                tile += 4 * 33;
+                tile += 4 * kLaneTS;
             }
-            j0 -= 32;
-            tile -= 32 * 33;
         } else {
 #pragma unroll 1
-            for (int i = 0; i < 32; i++) {
-                if (j0 < ncodes) VC2B_LANE_STEP(0)
+            for (int i = 0; i < kLaneChunk; i++) {
+                if (j0 < ncodes) VC2B_LANE_STEP(0, true)
                 if (R.avail < 32) lane_refill(R);
                 j0 += 1;
-                tile += 33;
+                tile += kLaneTS;
             }
-            j0 -= 32;
-            tile -= 32 * 33;
         }
+        j0 -= kLaneChunk;
+        tile -= kLaneChunk * kLaneTS;
         __syncwarp();
 
-        // ---- store: per slice, lane = coefficient --------------------------------------------------
-        const int j = j0 + lane;
+        // ---- store: two slices per instruction, 16 consecutive codes each ---------------------------
+        const int j = j0 + c;
         const int jj = j >> I;
         const uint32_t loc = j < refcodes ? S.map[mc][jj] : 0u;
         const int mb = loc >> 26, moff = loc & 0x3ffffffu;
@@ -362,38 +370,37 @@ __device__ __forceinline__ void lanes_block(const DevParams &P, const int comp, 
         if (uniform) {
             if (j < refcodes) {
                 int32_t *p = dst + moff;
-                const int32_t *tb = &W.tile[lane * 33];
-                const int32_t *bb = &W.base[mb];
+                const int32_t *tb = &W.tile[c * kLaneTS + h];
+                const int32_t *bb = &W.base[h * kLaneBaseStride + mb];
                 if (act_mask == 0xffffffffu) {
 #pragma unroll
-                    for (int s = 0; s < 32; s++) p[bb[s * kLaneBaseStride]] = tb[s];
+                    for (int k = 0; k < 16; k++) p[bb[2 * k * kLaneBaseStride]] = tb[2 * k];
                 } else {
 #pragma unroll 4
-                    for (int s = 0; s < 32; s++)
-                        if ((act_mask >> s) & 1) p[bb[s * kLaneBaseStride]] = tb[s];
+                    for (int k = 0; k < 16; k++)
+                        if ((act_mask >> (2 * k + h)) & 1) p[bb[2 * k * kLaneBaseStride]] = tb[2 * k];
                 }
             }
         } else {
-            for (int s = 0; s < 32; s++) {
+            for (int k = 0; k < 16; k++) {
+                const int s = 2 * k + h;
+                const int ncodes_s = __shfl_sync(0xffffffffu, ncodes, s);
                 if (!((act_mask >> s) & 1)) continue;
                 if ((match_mask >> s) & 1) {
-                    if (j < refcodes) dst[W.base[s * kLaneBaseStride + mb] + moff] = W.tile[lane * 33 + s];
-                } else {
-                    const int ncodes_s = __shfl_sync(0xffffffffu, ncodes, s);
-                    if (j < ncodes_s) {
-                        int bb = 0, cum = 0;
-                        uint32_t cw = W.cntw[0][s];
-                        while (jj >= cum + (int)(cw & 0xffffu)) {
-                            cum += (int)(cw & 0xffffu);
-                            bb++;
-                            cw = W.cntw[bb][s];
-                        }
-                        const int local = jj - cum;
-                        const int w = (int)(cw >> 16);
-                        const int y = local / w;
-                        const int x = local - y * w;
-                        dst[W.base[s * kLaneBaseStride + bb] + y * P.band[comp][bb].w + x] = W.tile[lane * 33 + s];
+                    if (j < refcodes) dst[W.base[s * kLaneBaseStride + mb] + moff] = W.tile[c * kLaneTS + s];
+                } else if (j < ncodes_s) {
+                    int bb = 0, cum = 0;
+                    uint32_t cw = W.cntw[0][s];
+                    while (jj >= cum + (int)(cw & 0xffffu)) {
+                        cum += (int)(cw & 0xffffu);
+                        bb++;
+                        cw = W.cntw[bb][s];
                     }
+                    const int local = jj - cum;
+                    const int w = (int)(cw >> 16);
+                    const int y = local / w;
+                    const int x = local - y * w;
+                    dst[W.base[s * kLaneBaseStride + bb] + y * P.band[comp][bb].w + x] = W.tile[c * kLaneTS + s];
                 }
             }
         }
@@ -452,7 +459,7 @@ __device__ __forceinline__ void build_lane_block(const DevParams &P, LaneBlock &
 
 // One LANE per slice; a warp task is 32 consecutive slices of one picture.
 template <bool LD>
-__global__ void __launch_bounds__(kLaneWarps * 32)
+__global__ void __launch_bounds__(kLaneWarps * 32, 6)
 unpack_lanes_kernel(DevParams P, const uint8_t *__restrict__ data, const int64_t *__restrict__ pic_offset,
                     int npictures, const uint32_t *__restrict__ slice_offset, int32_t *__restrict__ coeffs,
                     int32_t *__restrict__ qindex_out, int32_t *__restrict__ status)
