@@ -36,3 +36,20 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(params=["auto", "warp"])
+def unpack_kernel(request):
+    """Runs a test once with the library's own choice of unpack kernel (lane-per-slice where the
+    slices are small) and once with the warp-per-slice kernel forced (VC2B_UNPACK, read by
+    vc2b_unpack at every call)."""
+    old = os.environ.get("VC2B_UNPACK")
+    if request.param == "auto":
+        os.environ.pop("VC2B_UNPACK", None)
+    else:
+        os.environ["VC2B_UNPACK"] = request.param
+    yield request.param
+    if old is None:
+        os.environ.pop("VC2B_UNPACK", None)
+    else:
+        os.environ["VC2B_UNPACK"] = old

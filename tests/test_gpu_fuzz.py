@@ -35,7 +35,7 @@ CASES = [_random_case(np.random.RandomState(1000 + i)) for i in range(48)]
 
 
 @pytest.mark.parametrize("k", range(len(CASES)))
-def test_fuzz_decode_encode_vs_oracle(k):
+def test_fuzz_decode_encode_vs_oracle(k, unpack_kernel):
     import ctypes as C
 
     import oracle as O

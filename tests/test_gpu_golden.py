@@ -16,7 +16,7 @@ def _params(z, name):
 
 
 @pytest.mark.parametrize("name", picture_case_names())
-def test_decode_golden_pictures(name):
+def test_decode_golden_pictures(name, unpack_kernel):
     from vc2_conformance_b200.device import BatchCodec
 
     z = load("pictures")
@@ -38,7 +38,7 @@ def test_decode_golden_pictures(name):
 
 
 @pytest.mark.parametrize("name", picture_case_names())
-def test_decode_corrupt_streams(name):
+def test_decode_corrupt_streams(name, unpack_kernel):
     """Dangling / truncated bounded blocks, garbage lengths, end of stream
     (vc2_conformance/test_cases/decoder/pictures.py:351-472 semantics)."""
     import ctypes as C

@@ -48,7 +48,7 @@ HQ_CASES = [
 
 
 @pytest.mark.parametrize("case", HQ_CASES)
-def test_hq_batch_vs_oracle(case):
+def test_hq_batch_vs_oracle(case, unpack_kernel):
     from vc2_conformance_b200.device import BatchCodec
 
     import oracle as O
@@ -88,7 +88,7 @@ LD_CASES = [
 
 
 @pytest.mark.parametrize("case", LD_CASES)
-def test_ld_batch_vs_oracle(case):
+def test_ld_batch_vs_oracle(case, unpack_kernel):
     from vc2_conformance_b200.device import BatchCodec
     from vc2_conformance_b200.params import copy_params
 
