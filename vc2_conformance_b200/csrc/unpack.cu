@@ -991,7 +991,7 @@ int vc2b_unpack(const vc2b_params *p, const uint8_t *d_data, const int64_t *d_pi
     if (lanes) {
         const long long tasks = (long long)npictures * ((P.slices_x * P.slices_y + 31) / 32);
         long long nblk = (tasks + kLaneWarps - 1) / kLaneWarps;
-        const long long max_blocks = 148LL * 6;  // persistent: 6 CTAs per SM are resident (33 KB shared each)
+        const long long max_blocks = 148LL * 6;  // persistent: 6 CTAs per SM are resident (80 registers, 25 KB shared each)
         if (nblk > max_blocks) nblk = max_blocks;
         if (P.is_ld)
             unpack_lanes_kernel<true><<<(unsigned)nblk, kLaneWarps * 32, 0, s>>>(P, d_data, d_pic_offset, npictures,

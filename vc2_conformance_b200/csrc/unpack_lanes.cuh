@@ -32,7 +32,6 @@ constexpr int kLaneTS = 34;              // tile row stride: conflict-free for b
 struct LaneWarp {                        // per-warp shared memory
     int32_t tile[kLaneChunk * kLaneTS];  // [code of the chunk][slice]
     int32_t base[32 * kLaneBaseStride];  // [slice][band]: offset of the rectangle in the component
-    uint32_t cntw[kLaneBands][32];       // [band][slice]: coefficients | width << 16
 };
 
 struct LaneBlock {                       // per-CTA shared memory
@@ -41,14 +40,18 @@ struct LaneBlock {                       // per-CTA shared memory
     int32_t ref_h[2][kLaneBands];
     int32_t even_x[2][kLaneBands];       // ref_w if the band divides evenly between the slices, else -1
     int32_t even_y[2][kLaneBands];
+    int32_t ref_cnt[2][kLaneBands];      // ref_w * ref_h
     int32_t ref_ncoef[2];
-    uint16_t slut[256];                  // 8-bit window -> length | negative << 7 | magnitude << 8
+    uint32_t slut[256];                  // 8-bit window -> 2^length | magnitude << 16 | sign << 30 (0: longer code)
     uint2 qtab[kQTab];
 };
 
 // Codes that fit an 8-bit window, sign included: 0 -> "1"; +-1..2 -> 4 bits; +-3..6 -> 6 bits;
-// +-7..14 -> 8 bits (decoder/io.py:285-313).  Length 0 marks a longer code.
-__device__ __forceinline__ void build_lane_lut(uint16_t *slut, int tid, int nthreads)
+// +-7..14 -> 8 bits (decoder/io.py:285-313).  The entry is laid out for cheap field extraction on two
+// different pipes (the INT ALU pipe is the one that saturates): bits 0-8 = 2^length, so consuming the
+// code is a multiplication of the bit buffer; bits 16-23 = magnitude; bits 30-31 = sign as a two-bit
+// signed number (+1, 0, -1), read with one signed multiply-high.  0 marks a longer code.
+__device__ __forceinline__ void build_lane_lut(uint32_t *slut, int tid, int nthreads)
 {
     for (int e = tid; e < 256; e += nthreads) {
         int value = 1, pos = 7;
@@ -64,10 +67,14 @@ __device__ __forceinline__ void build_lane_lut(uint16_t *slut, int tid, int nthr
         }
         if (done) {
             value -= 1;
-            if (value == 0) entry = 1;
-            else if (pos >= 0) entry = (uint32_t)(8 - pos) | ((uint32_t)value << 8) | (((e >> pos) & 1) << 7);
+            if (value == 0) {
+                entry = 2u;  // one bit, value 0, sign 0
+            } else if (pos >= 0) {
+                const uint32_t sgn = ((e >> pos) & 1) ? 3u : 1u;
+                entry = (1u << (8 - pos)) | ((uint32_t)value << 16) | (sgn << 30);
+            }
         }
-        slut[e] = (uint16_t)entry;
+        slut[e] = entry;
     }
 }
 
@@ -115,12 +122,17 @@ __device__ __forceinline__ void lane_reader_init(LaneReader &R, const uint8_t *b
     long long rem = nbits + skip;
     if (rem > (1LL << 30)) rem = 1LL << 30;           // a slice of this kernel never reads that far
     R.remaining = active ? (int)rem : 0;
+    // the first three words are fetched together (one load latency, not three)
+    uint32_t raw0 = 0, raw1 = 0;
     R.ahead = 0;
-    lane_fetch(R);
-    const uint32_t w0 = lane_ahead_bits(R);
-    lane_fetch(R);
-    const uint32_t w1 = lane_ahead_bits(R);
-    lane_fetch(R);
+    if (R.remaining > 0) raw0 = __ldg(R.wp);
+    if (R.remaining > 32) raw1 = __ldg(R.wp + 1);
+    if (R.remaining > 64) R.ahead = __ldg(R.wp + 2);
+    uint32_t w0 = __byte_perm(raw0, 0, 0x0123), w1 = __byte_perm(raw1, 0, 0x0123);
+    if (R.remaining < 32) w0 |= 0xffffffffu >> max(R.remaining, 0);
+    if (R.remaining < 64) w1 |= 0xffffffffu >> max(R.remaining - 32, 0);
+    R.wp += 3;
+    R.remaining -= 96;
     R.buf = (((uint64_t)w0 << 32) | w1) << skip;
     R.avail = 64 - skip;
 }
@@ -193,11 +205,21 @@ __device__ __noinline__ LaneLong lane_read_long_cold(LaneReader R)
     return o;
 }
 
-__device__ __forceinline__ uint32_t lds_u16(uint32_t addr)
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
 {
-    uint16_t v;
-    asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
+}
+
+// Width | height << 16 of the rectangle of slice (sx, sy) in a band of bw x bh (slice_left/right/
+// top/bottom, pseudocode/slice_sizes.py:108-127).  Out of line: only slices of ragged geometries
+// whose rectangles differ from slice (0, 0)'s come here.
+__device__ __noinline__ uint32_t lane_rect_wh(int bw, int bh, int nx, int ny, int sx, int sy)
+{
+    const int x1 = (int)(((long long)bw * sx) / nx), x2 = (int)(((long long)bw * (sx + 1)) / nx);
+    const int y1 = (int)(((long long)bh * sy) / ny), y2 = (int)(((long long)bh * (sy + 1)) / ny);
+    return (uint32_t)(x2 - x1) | ((uint32_t)(y2 - y1) << 16);
 }
 
 // Decodes one bounded block per lane (component `comp` of the lane's slice) and scatters the
@@ -251,7 +273,6 @@ __device__ __forceinline__ void lanes_block(const DevParams &P, const int comp, 
             match = match && (w == S.ref_w[mc][b]) && (h == S.ref_h[mc][b]);
         }
         W.base[lane * kLaneBaseStride + b] = base;
-        W.cntw[b][lane] = (uint32_t)(w * h) | ((uint32_t)w << 16);
         ncoef += w * h;
     }
     const int ncodes = ncoef << I;
@@ -263,6 +284,7 @@ __device__ __forceinline__ void lanes_block(const DevParams &P, const int comp, 
     __syncwarp();
     if (act_mask == 0) return;
     const bool uniform = match_mask == act_mask;  // every lane decodes the reference rectangle
+    const bool my_match = match || !active;
 
     LaneReader R;
     lane_reader_init(R, blk, bit_off, nbits, active);
@@ -286,6 +308,14 @@ __device__ __forceinline__ void lanes_block(const DevParams &P, const int comp, 
         maxmag = 0;                                                                                  \
     }
 
+    // `mark` is multiplied by 2^length with the buffer, so the bits consumed since the last settle
+    // are log2(mark): avail is only needed at refills and on the long-code path.
+#define VC2B_LANE_SETTLE()                                                                           \
+    {                                                                                                \
+        R.avail -= mark ? 31 - __clz(mark) : 32;                                                     \
+        mark = 1;                                                                                    \
+    }
+
     // one code: read_sintb + inverse_quant, value to tile row i
 #define VC2B_LANE_STEP(i, CHK)                                                                       \
     {                                                                                                \
@@ -293,7 +323,13 @@ __device__ __forceinline__ void lanes_block(const DevParams &P, const int comp, 
             VC2B_LANE_CLOSE_BAND()                                                                   \
             do {                                                                                     \
                 b++;                                                                                 \
-                next += (int)(W.cntw[b][lane] & 0xffffu) << I;                                       \
+                int cnt = S.ref_cnt[mc][b];                                                          \
+                if (!my_match) {                                                                     \
+                    const uint32_t wh = lane_rect_wh(P.band[comp][b].w, P.band[comp][b].h, P.slices_x, \
+                                                     P.slices_y, sx, sy);                            \
+                    cnt = (int)(wh & 0xffffu) * (int)(wh >> 16);                                     \
+                }                                                                                    \
+                next += cnt << I;                                                                    \
             } while (j0 + (i) == next);                                                              \
             const int q = max(qindex - P.band[comp][b].qm, 0);                                       \
             const uint2 qq = S.qtab[min(q, kQTab - 1)];                                              \
@@ -301,32 +337,33 @@ __device__ __forceinline__ void lanes_block(const DevParams &P, const int comp, 
             qo = qq.y;                                                                               \
         }                                                                                            \
         const uint32_t hi = (uint32_t)(R.buf >> 32);                                                 \
-        const uint32_t e = lds_u16(slut_addr + 2 * __byte_perm(hi, 0, 0x4443));                     \
-        const int len = e & 15;                                                                      \
-        uint32_t mag = e >> 8, neg = e & 0x80;                                                       \
-        if (__builtin_expect(len == 0, 0)) {                                                         \
+        const uint32_t e = lds_u32(slut_addr + 4 * (hi >> 24));                                      \
+        const uint32_t M = e & 0x1ffu;                                                               \
+        uint32_t mag = __byte_perm(e, 0, 0x4442);                                                    \
+        int sgn = __mulhi((int)e, 4);  /* e >> 30, arithmetic, on the multiplier pipe */             \
+        if (__builtin_expect(M == 0, 0)) {                                                           \
+            VC2B_LANE_SETTLE()                                                                       \
             const LaneLong o = lane_read_long_cold(R);                                               \
             R = o.R;                                                                                 \
             mag = o.mag;                                                                             \
-            neg = o.neg;                                                                             \
+            sgn = o.neg ? -1 : 1;                                                                    \
             if (!o.ok) {                                                                             \
                 bad |= 1u;                                                                           \
                 lane_reader_kill(R);                                                                 \
             }                                                                                        \
         } else {                                                                                     \
-            R.buf <<= len;                                                                           \
-            R.avail -= len;                                                                          \
+            R.buf *= M;                                                                              \
+            mark *= M;                                                                               \
         }                                                                                            \
-        /* inverse_quant (pseudocode/quantization.py:18): (m*qf + qo + 2) // 4, zero stays zero */   \
-        const uint32_t qoe = mag ? qo : 0u;                                                          \
-        const uint32_t t = (uint32_t)(((unsigned long long)mag * qf + qoe) >> 2);                    \
+        /* inverse_quant (pseudocode/quantization.py:18): (m*qf + qo + 2) // 4; sign 0 keeps zero zero */ \
+        const uint32_t t = (uint32_t)(((unsigned long long)mag * qf + qo) >> 2);                     \
         maxmag = max(maxmag, mag);                                                                   \
-        tile[(i) * kLaneTS] = neg ? -(int32_t)t : (int32_t)t;                                        \
+        tile[(i) * kLaneTS] = (int32_t)t * sgn;                                                      \
     }
 
     // the int32 envelope was left if some m*qf+qo reached 2^33 (hiacc >= 2), a non-zero value met a
     // saturated quantiser or a value had 32 or more data bits (bad != 0)
-    uint32_t hiacc = 0, bad = 0;
+    uint32_t hiacc = 0, bad = 0, mark = 1;
     const int c = lane & 15, h = lane >> 4;   // store phase: half-warp h takes slice 2k+h, lane c its code c
     for (int j0 = 0; j0 < jmax; j0 += kLaneChunk) {
         // ---- decode: lane = slice, kLaneChunk codes each -------------------------------------------
@@ -344,6 +381,7 @@ __device__ __forceinline__ void lanes_block(const DevParams &P, const int comp, 
                     VC2B_LANE_STEP(2, true)
                     VC2B_LANE_STEP(3, true)
                 }
+                VC2B_LANE_SETTLE()
                 lane_refill(R);
                 j0 += 4;
                 tile += 4 * kLaneTS;
@@ -352,6 +390,7 @@ __device__ __forceinline__ void lanes_block(const DevParams &P, const int comp, 
 #pragma unroll 1
             for (int i = 0; i < kLaneChunk; i++) {
                 if (j0 < ncodes) VC2B_LANE_STEP(0, true)
+                VC2B_LANE_SETTLE()
                 if (R.avail < 32) lane_refill(R);
                 j0 += 1;
                 tile += kLaneTS;
@@ -369,35 +408,40 @@ __device__ __forceinline__ void lanes_block(const DevParams &P, const int comp, 
         int32_t *dst = (INTERLEAVED && (j & 1)) ? out2 : out;
         if (uniform) {
             if (j < refcodes) {
-                int32_t *p = dst + moff;
+                // one 64-bit multiply-add per address: byte pointer + 4 * (unsigned) rectangle offset
+                char *p = reinterpret_cast<char *>(dst + moff);
                 const int32_t *tb = &W.tile[c * kLaneTS + h];
                 const int32_t *bb = &W.base[h * kLaneBaseStride + mb];
                 if (act_mask == 0xffffffffu) {
 #pragma unroll
-                    for (int k = 0; k < 16; k++) p[bb[2 * k * kLaneBaseStride]] = tb[2 * k];
+                    for (int k = 0; k < 16; k++)
+                        *reinterpret_cast<int32_t *>(p + 4ull * (uint32_t)bb[2 * k * kLaneBaseStride]) = tb[2 * k];
                 } else {
 #pragma unroll 4
                     for (int k = 0; k < 16; k++)
-                        if ((act_mask >> (2 * k + h)) & 1) p[bb[2 * k * kLaneBaseStride]] = tb[2 * k];
+                        if ((act_mask >> (2 * k + h)) & 1)
+                            *reinterpret_cast<int32_t *>(p + 4ull * (uint32_t)bb[2 * k * kLaneBaseStride]) = tb[2 * k];
                 }
             }
         } else {
             for (int k = 0; k < 16; k++) {
                 const int s = 2 * k + h;
                 const int ncodes_s = __shfl_sync(0xffffffffu, ncodes, s);
+                const int sxs = __shfl_sync(0xffffffffu, sx, s), sys = __shfl_sync(0xffffffffu, sy, s);
                 if (!((act_mask >> s) & 1)) continue;
                 if ((match_mask >> s) & 1) {
                     if (j < refcodes) dst[W.base[s * kLaneBaseStride + mb] + moff] = W.tile[c * kLaneTS + s];
                 } else if (j < ncodes_s) {
+                    // locate code j in slice s's own rectangles
                     int bb = 0, cum = 0;
-                    uint32_t cw = W.cntw[0][s];
-                    while (jj >= cum + (int)(cw & 0xffffu)) {
-                        cum += (int)(cw & 0xffffu);
+                    uint32_t wh = lane_rect_wh(P.band[comp][0].w, P.band[comp][0].h, P.slices_x, P.slices_y, sxs, sys);
+                    while (jj >= cum + (int)(wh & 0xffffu) * (int)(wh >> 16)) {
+                        cum += (int)(wh & 0xffffu) * (int)(wh >> 16);
                         bb++;
-                        cw = W.cntw[bb][s];
+                        wh = lane_rect_wh(P.band[comp][bb].w, P.band[comp][bb].h, P.slices_x, P.slices_y, sxs, sys);
                     }
                     const int local = jj - cum;
-                    const int w = (int)(cw >> 16);
+                    const int w = (int)(wh & 0xffffu);
                     const int y = local / w;
                     const int x = local - y * w;
                     dst[W.base[s * kLaneBaseStride + bb] + y * P.band[comp][bb].w + x] = W.tile[c * kLaneTS + s];
@@ -408,6 +452,7 @@ __device__ __forceinline__ void lanes_block(const DevParams &P, const int comp, 
     }
     VC2B_LANE_CLOSE_BAND()
 #undef VC2B_LANE_STEP
+#undef VC2B_LANE_SETTLE
 #undef VC2B_LANE_CLOSE_BAND
     if ((hiacc >> 1) != 0 || bad != 0) ovf = true;
 }
@@ -428,6 +473,7 @@ __device__ __forceinline__ void build_lane_block(const DevParams &P, LaneBlock &
         }
         S.ref_w[mc][b] = rw;
         S.ref_h[mc][b] = rh;
+        S.ref_cnt[mc][b] = rw * rh;
         S.even_x[mc][b] = ex;
         S.even_y[mc][b] = ey;
     }
