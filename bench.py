@@ -79,7 +79,7 @@ WORKLOADS = {
 # captures of these kernels on this workload; the summaries are committed under profiles/.
 NCU_TRAFFIC_PER_PICTURE = {
     "cfg2": {
-        "unpack": (87.2e6, "profiles/r1_v5_unpack_ncu_full_raw.csv (unpack_hq_kernel, 64 pictures)"),
+        "unpack": (70.9e6, "profiles/r1_v7_unpack_lanes_ncu_full_raw.csv (unpack_lanes_kernel, 32 pictures)"),
         "idwt": (144.0e6, "profiles/r1_v4_idwt_levels_ncu.csv (4 idwt_stream8_kernel launches, 16 pictures)"),
     },
 }
@@ -475,7 +475,8 @@ def run_ours(args):
     stages = {
         "unpack": {"ms_per_step": ms_unpack, "achieved": unpack_gbs, "frac": unpack_gbs / peak,
                    "algorithmic_bytes_per_picture": unpack_bytes // NP,
-                   "kernels": "hq_walk_kernel + unpack_hq_kernel" if not p.is_ld else "unpack_ld_kernel + dc_prediction_kernel"},
+                   "kernels": "hq_walk_kernel + unpack_lanes_kernel<HQ>" if not p.is_ld
+                   else "unpack_lanes_kernel<LD> + dc_prediction_kernel"},
         "idwt": {"ms_per_step": ms_idwt, "achieved": idwt_gbs, "frac": idwt_gbs / peak,
                  "algorithmic_bytes_per_picture": idwt_bytes // NP,
                  "kernels": "idwt_stream8_kernel x %d levels (last fused with crop+clip+offset)"
