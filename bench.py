@@ -2,7 +2,7 @@
 """
 bench.py -- decoded pictures/s of the VC-2 picture path on B200 (BASELINE.json metric).
 
-    python bench.py --gpus 1 --steps 5 --warmup 3
+    python bench.py --gpus 1 --steps 20 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference            # the CPU arm (oracle port on all host cores)
 
@@ -88,7 +88,7 @@ NCU_TRAFFIC_PER_PICTURE = {
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
@@ -140,22 +140,78 @@ def synth_pictures(w, first, count):
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons sampled DURING the timed regions (B200_PROFILING.md clocks line):
+    NVML polled every 2 ms from a thread (nvidia_ml_py); nvidia-smi -lms as the fallback."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index):
+    def __init__(self, index, uuid=None):
         self.index = index
-        self.samples = []
+        self.uuid = uuid
+        self.samples = []   # (time, sm_mhz, sm_max_mhz, [reasons])
         self.proc = None
+        self.thread = None
+        self.running = False
+        self.source = None
+
+    def _nvml_handle(self):
+        import pynvml as N
+
+        N.nvmlInit()
+        if self.uuid:
+            try:
+                return N, N.nvmlDeviceGetHandleByUUID(("GPU-" + str(self.uuid)).encode())
+            except Exception:
+                pass
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        idx = self.index
+        if vis:
+            try:
+                idx = int(vis.split(",")[self.index])
+            except Exception:
+                pass
+        return N, N.nvmlDeviceGetHandleByIndex(idx)
+
+    def _poll_nvml(self, N, h):
+        bits = [(N.nvmlClocksEventReasonHwSlowdown, "hw_slowdown"),
+                (N.nvmlClocksEventReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                (N.nvmlClocksEventReasonSwThermalSlowdown, "sw_thermal_slowdown"),
+                (N.nvmlClocksEventReasonSwPowerCap, "sw_power_cap")]
+        try:
+            smmax = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+        except Exception:
+            smmax = 0.0
+        while self.running:
+            try:
+                sm = float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM))
+                try:
+                    mask = N.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    mask = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((time.time(), sm, smmax, [n for b, n in bits if mask & b]))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        try:
+            N, h = self._nvml_handle()
+            N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+            self.running = True
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._poll_nvml, args=(N, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.running = False
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
                  "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -163,9 +219,16 @@ class ClockSampler(object):
 
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append((time.time(), line.strip()))
+            f = [x.strip() for x in line.strip().split(",")]
+            try:
+                sm, smmax = float(f[0]), float(f[1])
+            except Exception:
+                continue
+            self.samples.append((time.time(), sm, smmax,
+                                 [n for n, v in zip(self.NAMES, f[3:7]) if v.lower().startswith("active")]))
 
     def stop(self):
+        self.running = False
         if self.proc is not None:
             self.proc.terminate()
             try:
@@ -173,25 +236,19 @@ class ClockSampler(object):
             except Exception:
                 self.proc.kill()
 
-    def summary(self, t0, t1):
+    def summary(self, windows):
+        """windows: [(t0, t1), ...] wall-clock bounds of the timed regions"""
         sm, smmax, reasons = [], 0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for t, line in self.samples:
-            if t < t0 - 0.05 or t > t1 + 0.05:
+        for t, f, fmax, rs in list(self.samples):
+            if not any(t0 <= t <= t1 for t0, t1 in windows):
                 continue
-            f = [x.strip() for x in line.split(",")]
-            try:
-                sm.append(float(f[0]))
-                smmax = max(smmax, float(f[1]))
-            except Exception:
-                continue
-            for nme, val in zip(names, f[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(nme)
+            sm.append(f)
+            smmax = max(smmax, fmax)
+            reasons.update(rs)
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": smmax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": self.source}
+        return {"sm_mhz": float(np.median(sm)), "sm_min_mhz": float(min(sm)), "sm_max_mhz": smmax,
+                "reasons": sorted(reasons), "samples": len(sm), "source": self.source}
 
 
 def measured_peak():
@@ -378,7 +435,11 @@ def run_ours(args):
     assert (st[:, 0] == 0).all(), "decode status not OK"
     assert (st[:, 2] == np.diff(offs.numpy())).all(), "consumed bytes mismatch"
 
-    sampler = ClockSampler(local_rank)
+    try:
+        uuid = torch.cuda.get_device_properties(local_rank).uuid
+    except Exception:
+        uuid = None
+    sampler = ClockSampler(local_rank, uuid)
     sampler.start()
 
     # ---- device-resident timed region --------------------------------------------------------
@@ -404,12 +465,10 @@ def run_ours(args):
             capi.check("vc2b_hq_slice_offsets",
                        L.vc2b_hq_slice_offsets(C.byref(p), _ptr(codec.data), _ptr(codec.pic_offset), NP,
                                                _ptr(codec.slice_offset), _ptr(codec.status), sp))
-            codec.launches += 1
         capi.check("vc2b_unpack",
                    L.vc2b_unpack(C.byref(p), _ptr(codec.data), _ptr(codec.pic_offset), NP,
                                  _ptr(codec.slice_offset), _ptr(codec.coeffs), _ptr(codec.qindex),
                                  _ptr(codec.status), sp))
-        codec.launches += 4 if p.is_ld else 2
         ev[k][1].record(cur)
         codec.idwt_device(NP)
         ev[k][2].record(cur)
@@ -425,7 +484,7 @@ def run_ours(args):
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms_max = float(t_ms.item())
     value = world * NP * args.steps / (ms_max / 1000.0)
-    clocks = sampler.summary(t_wall0, t_wall1)
+    clock_windows = [(t_wall0, t_wall1)]
 
     # ---- end-to-end timed region (host buffers) ----------------------------------------------
     e2e = None
@@ -445,6 +504,7 @@ def run_ours(args):
         assert torch.equal(out_host[NP - 1].view(torch.int16), ref_last.view(torch.int16)), "e2e output mismatch"
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = seq.launches
+        t_e2e0 = time.time()
         s0.record(cur)
         for _ in range(args.steps):
             seq.fork_from(cur)
@@ -452,6 +512,7 @@ def run_ours(args):
             seq.join_to(cur)
         s1.record(cur)
         barrier()
+        clock_windows.append((t_e2e0, time.time()))
         e2e_ms = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
@@ -464,6 +525,7 @@ def run_ours(args):
             "pipeline": "%d-picture chunks over 3 CUDA streams" % chunk,
         }
     sampler.stop()
+    clocks = sampler.summary(clock_windows)
 
     # ---- roofline of the stages (algorithmic bytes) -----------------------------
     peak, peak_src = measured_peak()

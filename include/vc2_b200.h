@@ -65,6 +65,9 @@ typedef struct vc2b_params {
 
 /* ---- introspection --------------------------------------------------------------- */
 const char *vc2b_version(void);
+/* Number of CUDA kernels this library has launched in this process so far (every launch site
+ * counts; bench.py reports the difference across its timed region as gpu_launches). */
+int64_t vc2b_launch_count(void);
 /* Checks a parameter set; 0 if the library supports it. */
 int vc2b_check_params(const vc2b_params *p);
 /* Subband geometry (pseudocode/slice_sizes.py:53-92).  Subbands are numbered in bitstream

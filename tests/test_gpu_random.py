@@ -226,3 +226,31 @@ def test_full_size_ld_field():
     flat = np.stack([synth.flat_picture(pl) for pl in pics])
     out = codec.encode_pictures(flat, 0)
     assert out[0] == streams[0] and out[1] == streams[1]
+
+
+@pytest.mark.parametrize("case", [HQ_CASES[0], HQ_CASES[2], HQ_CASES[4]])
+def test_idwt_l2_subgroups(case, monkeypatch):
+    """The last two IDWT levels run over L2-sized sub-groups of pictures through shared scratch slots
+    (idwt.cu run_idwt); every sub-group size and hint mode must give the oracle's pictures."""
+    from vc2_conformance_b200.device import BatchCodec
+
+    import oracle as O
+
+    W, H, cw, ch, depth, wi, wiho, d, dho, sx, sy, scaler = case
+    S = W * H + 2 * cw * ch
+    scaler = max(scaler, O.safe_lossy_hq_slice_size_scaler(2 * S, sx * sy))
+    p = _mk(luma_width=W, luma_height=H, color_diff_width=cw, color_diff_height=ch, luma_depth=depth,
+            wavelet_index=wi, wavelet_index_ho=wiho, dwt_depth=d, dwt_depth_ho=dho, slices_x=sx, slices_y=sy,
+            slice_size_scaler=scaler)
+    pics = [synth.noise_picture(p, 20 + i) if i % 2 == 0 else synth.ramp_picture(p, 20 + i) for i in range(7)]
+    streams, decoded = _oracle_streams(p, pics, [S // 2] * len(pics))
+    for group, hints in [("0", "0"), ("1", "1"), ("2", "3"), ("3", "2"), ("5", "1")]:
+        monkeypatch.setenv("VC2B_IDWT_L2_GROUP", group)
+        monkeypatch.setenv("VC2B_IDWT_L2_HINTS", hints)
+        codec = BatchCodec(p, len(pics))
+        codec.pictures.view(codec.torch.int16).fill_(-1)
+        codec.decode_streams(streams)
+        for i in range(len(pics)):
+            planes = codec.picture_planes(i)
+            for c in range(3):
+                assert (planes[c] == decoded[i][c]).all(), (case, group, hints, i, c)

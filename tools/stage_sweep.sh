@@ -1,0 +1,9 @@
+#!/bin/bash
+# Device-timed stage micro-benchmarks over the BASELINE configurations (tools/bench_stage.py).
+cd "$(dirname "$0")/.."
+for wl in cfg1 cfg2 cfg3 cfg4; do
+  for st in unpack idwt; do python tools/bench_stage.py $st --workload $wl --pictures 64 2>&1 | tail -1; done
+done
+for wl in cfg2 cfg5; do
+  for st in dwt quant pack; do python tools/bench_stage.py $st --workload $wl --pictures 8 2>&1 | tail -1; done
+done

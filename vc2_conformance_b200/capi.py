@@ -69,6 +69,7 @@ _i64 = C.c_int64
 # name -> (restype, argtypes); every symbol include/vc2_b200.h declares
 SIGNATURES = {
     "vc2b_version": (C.c_char_p, []),
+    "vc2b_launch_count": (_i64, []),
     "vc2b_check_params": (_i, [_PP]),
     "vc2b_num_subbands": (_i, [_PP]),
     "vc2b_subband_info": (_i, [_PP, _i, _i, _vp, _vp, _vp, _vp, _vp]),

@@ -90,8 +90,12 @@ __host__ __device__ inline int64_t ld_slice_offset(const DevParams &P, int64_t n
     return (n * P.sb_num) / P.sb_den;
 }
 
+// kernels launched by the library (vc2b_launch_count); defined in params.cu
+extern unsigned long long g_launch_count;
+
 #define VC2B_CHECK_LAUNCH()                          \
     do {                                             \
+        __atomic_add_fetch(&vc2b::g_launch_count, 1ull, __ATOMIC_RELAXED); \
         cudaError_t e__ = cudaGetLastError();        \
         if (e__ != cudaSuccess) return (int)e__;     \
     } while (0)

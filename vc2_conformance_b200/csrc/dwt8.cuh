@@ -331,16 +331,31 @@ static int launch_ana_wide_steps(AnaArgs A, int npic, cudaStream_t s)
 template <int FV, int FH>
 static int launch_ana_wide(const AnaArgs &A, int npic, cudaStream_t s)
 {
-    long long warps64 = 0, warps32 = 0;
-    for (int c = 0; c < A.ncomp; c++) {
-        const long long tx = (A.W[c] + Ana8Cfg<FV, FH, 64>::WOUT - 1) / Ana8Cfg<FV, FH, 64>::WOUT;
-        warps64 += tx * (((A.H[c] >> 1) + Ana8Cfg<FV, FH, 64>::RSP - 1) / Ana8Cfg<FV, FH, 64>::RSP) * npic;
-        warps32 += tx * (((A.H[c] >> 1) + Ana8Cfg<FV, FH, 32>::RSP - 1) / Ana8Cfg<FV, FH, 32>::RSP) * npic;
+    // strip height by the same cost model as the synthesis launcher (idwt8.cuh launch_wide)
+    const double slots = 148.0 * 14;
+    double best = 0;
+    int pick = 64;
+    const int rsp[3] = {Ana8Cfg<FV, FH, 64>::RSP, Ana8Cfg<FV, FH, 32>::RSP, Ana8Cfg<FV, FH, 16>::RSP};
+    const int steps[3] = {64, 32, 16};
+    for (int k = 0; k < 3; k++) {
+        if (rsp[k] < 1) continue;
+        double warps = 0;
+        for (int c = 0; c < A.ncomp; c++) {
+            const long long tx = (A.W[c] + Ana8Cfg<FV, FH, 64>::WOUT - 1) / Ana8Cfg<FV, FH, 64>::WOUT;
+            warps += (double)tx * (((A.H[c] >> 1) + rsp[k] - 1) / rsp[k]) * npic;
+        }
+        const double waves = warps / slots;
+        const double cost = ((waves > 1 ? waves : 1) + 0.5) * steps[k];
+        if (best == 0 || cost < best) { best = cost; pick = steps[k]; }
     }
-    const long long want = 148LL * 14 * 3;
-    if (warps64 >= want) return launch_ana_wide_steps<FV, FH, 64>(A, npic, s);
-    if (warps32 >= want) return launch_ana_wide_steps<FV, FH, 32>(A, npic, s);
-    return launch_ana_wide_steps<FV, FH, 16>(A, npic, s);
+    if (pick == 64) return launch_ana_wide_steps<FV, FH, 64>(A, npic, s);
+    if constexpr (Ana8Cfg<FV, FH, 32>::RSP >= 1) {
+        if (pick == 32) return launch_ana_wide_steps<FV, FH, 32>(A, npic, s);
+    }
+    if constexpr (Ana8Cfg<FV, FH, 16>::RSP >= 1) {
+        if (pick == 16) return launch_ana_wide_steps<FV, FH, 16>(A, npic, s);
+    }
+    return launch_ana_wide_steps<FV, FH, 64>(A, npic, s);
 }
 
 }  // namespace vc2b

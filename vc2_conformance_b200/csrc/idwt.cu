@@ -19,6 +19,8 @@
 // (:301) and stores packed uint16.  Kernels: idwt_stream8_kernel (idwt8.cuh: 8 columns per lane,
 // cp.async staging; the fast path), idwt_stream_kernel (2 columns per lane; any width / filter
 // pair), idwt_rows_kernel (horizontal-only levels).
+#include <stdlib.h>
+
 #include "stream_lift.cuh"
 
 namespace vc2b {
@@ -42,6 +44,8 @@ struct LevelArgs {
     int32_t shift;                  // filter_bit_shift(wavelet_index_ho)
     int32_t tiles_x[3], tiles_y[3];
     int32_t ncomp;
+    int32_t hint_loads;                  // 1: the cp.async loads carry hint_ll / hint_hb
+    int32_t hint_ll, hint_hb, hint_out;  // L2Hint of the LL input, the high-pass inputs and the output (wide kernel)
 };
 
 // ---- horizontal lifting across lanes ---------------------------------------------------------
@@ -462,7 +466,42 @@ static void plan_scratch(const DevParams &P, int c0, int c1, ScratchPlan *sp)
     }
 }
 
+// How many pictures' worth of intermediate LL bands the last two levels keep in flight (see run_idwt).
+// VC2B_IDWT_L2_GROUP: 0 = off (every level runs over the whole group; the default), n = fixed
+// sub-group size, -1 = as many pictures as fit kL2BudgetBytes.  Measured on B200 (cfg2, 120 pictures,
+// gpurun_out/l2_sweep.log -> profiles/): sub-groups of 1 / 4 / 12 pictures run at 51 / 33 / 28 us per
+// picture against 24.9 for whole-group launches -- a sub-group is less than one wave of strips, so every
+// launch costs a full strip latency and the DRAM traffic saved does not pay for it.  Kept as an
+// experiment knob (and tested); the store hints alone are worth 3 %.
+// VC2B_IDWT_L2_HINTS: bit 0 eviction hints on the stores (default), bit 1 on the loads.
+constexpr long long kL2BudgetBytes = 40LL << 20;
+
+static int l2_subgroup(long long level_out_bytes_per_picture, int npic)
+{
+    const char *e = getenv("VC2B_IDWT_L2_GROUP");  // read per call: the tests switch it
+    const int forced = e ? atoi(e) : 0;
+    if (forced == 0) return npic;
+    long long g = forced > 0 ? forced : kL2BudgetBytes / (level_out_bytes_per_picture > 0 ? level_out_bytes_per_picture : 1);
+    if (g < 1) g = 1;
+    return g < npic ? (int)g : npic;
+}
+
+// bit 0: eviction hints on the stores, bit 1: on the loads
+static int l2_hints_enabled()
+{
+    const char *e = getenv("VC2B_IDWT_L2_HINTS");
+    return e ? atoi(e) : 1;
+}
+
 // Runs all levels for components [c0, c1) of `npic` pictures.
+//
+// Level order: levels 1 .. top-2 run over the whole group (their output is small).  The last two
+// levels -- whose intermediate band is a quarter of the picture, by far the largest -- run
+// alternately over sub-groups of pictures sized to the L2 (l2_subgroup): level top-1 writes the LL
+// band of the sub-group into the SAME scratch slots every time, level top reads it straight back.
+// With the streams tagged evict_first and this band evict_last, it is produced and consumed in L2
+// and its dirty lines are overwritten by the next sub-group instead of being written back, so the
+// band does not cost a DRAM round trip ("each level is not a separate HBM pass").
 static int run_idwt(const DevParams &P, int c0, int c1, const int32_t *coeffs, long long coeff_pic_stride,
                     int npic, uint16_t *pictures, int32_t *raw_out, int32_t *scratch, const ScratchPlan &sp,
                     cudaStream_t s)
@@ -481,11 +520,11 @@ static int run_idwt(const DevParams &P, int c0, int c1, const int32_t *coeffs, l
         A.crop_w[i] = P.width[c];
         A.crop_h[i] = P.height[c];
         A.depth[i] = P.depth[c];
-        if (pictures) A.pic[i] = pictures + P.pic_off[c];
     }
     if (top == 0) {
         for (int i = 0; i < ncomp; i++) {
             const int c = c0 + i;
+            if (pictures) A.pic[i] = pictures + P.pic_off[c];
             A.ll[i] = coeffs + P.comp_off[c] + P.band[c][0].off;
             A.ll_pic_stride[i] = coeff_pic_stride;
             A.w[i] = P.band[c][0].w;
@@ -499,7 +538,11 @@ static int run_idwt(const DevParams &P, int c0, int c1, const int32_t *coeffs, l
         VC2B_CHECK_LAUNCH();
         return 0;
     }
-    for (int n = 1; n <= top; n++) {
+    const bool hints = (l2_hints_enabled() & 1) && npic > 1;
+    A.hint_loads = (l2_hints_enabled() & 2) && npic > 1;
+    // Level n over pictures [first, first + cnt): its LL input sits in scratch slots ll_slot.. (or in
+    // the coefficients for n == 1), its output goes to scratch slots out_slot..
+    auto run_level = [&](int n, int first, int cnt, int ll_slot, int out_slot, bool resident_out) -> int {
         const bool vert = n > P.dwt_depth_ho;
         const bool last = n == top;
         const int fb = level_first_band(P, n);
@@ -511,17 +554,20 @@ static int run_idwt(const DevParams &P, int c0, int c1, const int32_t *coeffs, l
             A.w[i] = B.w;
             A.h[i] = B.h;
             for (int k = 0; k < (vert ? 3 : 1); k++)
-                A.hb[i][k] = coeffs + P.comp_off[c] + P.band[c][fb + k].off;
+                A.hb[i][k] = coeffs + (long long)first * coeff_pic_stride + P.comp_off[c] + P.band[c][fb + k].off;
+            A.pic[i] = pictures ? pictures + (long long)first * P.pic_samples + P.pic_off[c] : nullptr;
             if (n == 1) {
-                A.ll[i] = coeffs + P.comp_off[c] + P.band[c][0].off;
+                A.ll[i] = coeffs + (long long)first * coeff_pic_stride + P.comp_off[c] + P.band[c][0].off;
                 A.ll_pic_stride[i] = coeff_pic_stride;
             } else {
                 const int rsel = ((top - 1) - (n - 1)) & 1;
-                A.ll[i] = scratch + (rsel == 0 ? sp.comp_off_a[c] : sp.size_a + sp.comp_off_b[c]);
+                A.ll[i] = scratch + (long long)ll_slot * scratch_pic +
+                          (rsel == 0 ? sp.comp_off_a[c] : sp.size_a + sp.comp_off_b[c]);
                 A.ll_pic_stride[i] = scratch_pic;
             }
             if (!last) {
-                A.out[i] = scratch + (wsel == 0 ? sp.comp_off_a[c] : sp.size_a + sp.comp_off_b[c]);
+                A.out[i] = scratch + (long long)out_slot * scratch_pic +
+                           (wsel == 0 ? sp.comp_off_a[c] : sp.size_a + sp.comp_off_b[c]);
                 A.out_pic_stride[i] = scratch_pic;
             } else {
                 A.out[i] = raw_out;
@@ -529,7 +575,34 @@ static int run_idwt(const DevParams &P, int c0, int c1, const int32_t *coeffs, l
             }
         }
         A.final_u16 = (last && pictures) ? 1 : 0;
-        int st = launch_level(P.wavelet_index, P.wavelet_index_ho, vert, A, npic, s);
+        A.hint_hb = A.hint_loads ? kL2EvictFirst : kL2Normal;               // read once
+        A.hint_ll = (A.hint_loads && n == 1) ? kL2EvictFirst : kL2Normal;   // level-0 band: read once
+        A.hint_out = !hints ? kL2Normal : (last ? kL2EvictFirst : (resident_out ? kL2EvictLast : kL2Normal));
+        return launch_level(P.wavelet_index, P.wavelet_index_ho, vert, A, cnt, s);
+    };
+    long long out_bytes = 0;  // level top-1 output per picture
+    if (top >= 2)
+        for (int i = 0; i < ncomp; i++) {
+            const Band &B = P.band[c0 + i][level_first_band(P, top)];
+            out_bytes += 4LL * B.w * B.h;
+        }
+    const int sub = top >= 2 ? l2_subgroup(out_bytes, npic) : npic;
+    if (sub >= npic) {
+        for (int n = 1; n <= top; n++) {
+            int st = run_level(n, 0, npic, 0, 0, npic == 1 ? false : (n == top - 1 && out_bytes * npic <= kL2BudgetBytes));
+            if (st) return st;
+        }
+        return 0;
+    }
+    for (int n = 1; n <= top - 2; n++) {
+        int st = run_level(n, 0, npic, 0, 0, false);
+        if (st) return st;
+    }
+    for (int first = 0; first < npic; first += sub) {
+        const int cnt = npic - first < sub ? npic - first : sub;
+        int st = run_level(top - 1, first, cnt, first, 0, true);
+        if (st) return st;
+        st = run_level(top, first, cnt, 0, 0, false);
         if (st) return st;
     }
     return 0;

@@ -42,7 +42,7 @@ struct Strip8Cfg {
 struct Strip8Ctx {
     const WideVec *ll, *b0, *b1, *b2;  // row-major, w/NP vectors per row
     int wq, h, jq, jqc, lane, lane_lo, lane_hi;
-    bool lane_ok, hedge;
+    bool lane_ok, hedge, ld_hints;
     int shift, cadd, vmax;             // final: v = clamp((x + cadd) >> shift, 0, vmax)
     int rnd;
     uint16_t *pic;
@@ -50,6 +50,7 @@ struct Strip8Ctx {
     bool vec_store;
     int32_t *out;
     int W2;
+    uint64_t pol_ll, pol_hb, pol_out;  // L2 eviction policies of the LL input, the high-pass inputs and the output
 };
 
 struct RawPair {
@@ -63,10 +64,17 @@ __device__ __forceinline__ void stage_pair8(const Strip8Ctx &X, WideVec *smem, i
     const int sy = min(max(m, 0), X.h - 1);
     const int idx = sy * X.wq + X.jqc;
     WideVec *st = smem + ((((m % NS) + NS) % NS) * 4) * 32 + X.lane;
-    cp_async_vec(st, X.ll + idx);
-    cp_async_vec(st + 32, X.b0 + idx);
-    cp_async_vec(st + 64, X.b1 + idx);
-    cp_async_vec(st + 96, X.b2 + idx);
+    if (X.ld_hints) {
+        cp_async_vec(st, X.ll + idx, X.pol_ll);
+        cp_async_vec(st + 32, X.b0 + idx, X.pol_hb);
+        cp_async_vec(st + 64, X.b1 + idx, X.pol_hb);
+        cp_async_vec(st + 96, X.b2 + idx, X.pol_hb);
+    } else {
+        cp_async_vec(st, X.ll + idx);
+        cp_async_vec(st + 32, X.b0 + idx);
+        cp_async_vec(st + 64, X.b1 + idx);
+        cp_async_vec(st + 96, X.b2 + idx);
+    }
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
@@ -131,7 +139,7 @@ __device__ __forceinline__ void finish_row8(const Strip8Ctx &X, int gy, int (&E)
             }
             uint16_t *d = X.pic + (long long)gy * X.cw + NC * X.jq;
             if (X.vec_store && NC * X.jq + NC <= X.cw) {
-                *reinterpret_cast<WideUVec *>(d) = array_to_uvec(pk);
+                st_hint(d, array_to_uvec(pk), X.pol_out);
             } else {
 #pragma unroll
                 for (int i = 0; i < NP; i++) {
@@ -151,8 +159,8 @@ __device__ __forceinline__ void finish_row8(const Strip8Ctx &X, int gy, int (&E)
                 if (c1 < NP) lo[c1] = v1; else hi[c1 - NP] = v1;
             }
             WideVec *d = reinterpret_cast<WideVec *>(X.out + (long long)gy * X.W2 + NC * X.jq);
-            d[0] = array_to_vec(lo);
-            d[1] = array_to_vec(hi);
+            st_hint(d, array_to_vec(lo), X.pol_out);
+            st_hint(d + 1, array_to_vec(hi), X.pol_out);
         }
     }
 }
@@ -292,6 +300,10 @@ idwt_stream8_kernel(LevelArgs A)
     X.out = A.out[c] + (long long)pic * A.out_pic_stride[c];
     X.W2 = 2 * A.w[c];
     X.hedge = (X.lane_lo > 0) || (X.lane_hi < 31);
+    X.ld_hints = A.hint_loads != 0;
+    X.pol_ll = l2_policy(A.hint_ll);
+    X.pol_hb = l2_policy(A.hint_hb);
+    X.pol_out = l2_policy(A.hint_out);
     if (A.final_u16) run_strip8<FV, FH, true, STEPS>(X, smem, ty); else run_strip8<FV, FH, false, STEPS>(X, smem, ty);
     asm volatile("cp.async.wait_group 0;" ::: "memory");  // drain look-ahead copies before exit
 }
@@ -339,16 +351,34 @@ static int launch_wide_steps(LevelArgs A, int npic, cudaStream_t s)
 template <int FV, int FH>
 static int launch_wide(const LevelArgs &A, int npic, cudaStream_t s)
 {
-    long long warps64 = 0, warps32 = 0;
-    for (int c = 0; c < A.ncomp; c++) {
-        const long long tx = (2 * A.w[c] + Strip8Cfg<FV, FH, 64>::WOUT - 1) / Strip8Cfg<FV, FH, 64>::WOUT;
-        warps64 += tx * ((A.h[c] + Strip8Cfg<FV, FH, 64>::RSP - 1) / Strip8Cfg<FV, FH, 64>::RSP) * npic;
-        warps32 += tx * ((A.h[c] + Strip8Cfg<FV, FH, 32>::RSP - 1) / Strip8Cfg<FV, FH, 32>::RSP) * npic;
+    // A strip is a serial chain of STEPS steps of which RSP produce output (the rest is warm-up and
+    // pipeline drain: 14 of them for Fidelity, 4 for LeGall).  Estimated duration of the launch with
+    // strip height S: (waves of resident warps, at least one, plus half a wave of tail) x S steps;
+    // short strips win only while the launch is a few waves and their RSP / STEPS is still decent.
+    const double slots = 148.0 * 14;
+    double best = 0;
+    int pick = 64;
+    const int rsp[3] = {Strip8Cfg<FV, FH, 64>::RSP, Strip8Cfg<FV, FH, 32>::RSP, Strip8Cfg<FV, FH, 16>::RSP};
+    const int steps[3] = {64, 32, 16};
+    for (int k = 0; k < 3; k++) {
+        if (rsp[k] < 1) continue;
+        double warps = 0;
+        for (int c = 0; c < A.ncomp; c++) {
+            const long long tx = (2 * A.w[c] + Strip8Cfg<FV, FH, 64>::WOUT - 1) / Strip8Cfg<FV, FH, 64>::WOUT;
+            warps += (double)tx * ((A.h[c] + rsp[k] - 1) / rsp[k]) * npic;
+        }
+        const double waves = warps / slots;
+        const double cost = ((waves > 1 ? waves : 1) + 0.5) * steps[k];
+        if (best == 0 || cost < best) { best = cost; pick = steps[k]; }
     }
-    const long long want = 148LL * 14 * 3;  // about three waves of resident warps
-    if (warps64 >= want) return launch_wide_steps<FV, FH, 64>(A, npic, s);
-    if (warps32 >= want) return launch_wide_steps<FV, FH, 32>(A, npic, s);
-    return launch_wide_steps<FV, FH, 16>(A, npic, s);
+    if (pick == 64) return launch_wide_steps<FV, FH, 64>(A, npic, s);
+    if constexpr (Strip8Cfg<FV, FH, 32>::RSP >= 1) {
+        if (pick == 32) return launch_wide_steps<FV, FH, 32>(A, npic, s);
+    }
+    if constexpr (Strip8Cfg<FV, FH, 16>::RSP >= 1) {
+        if (pick == 16) return launch_wide_steps<FV, FH, 16>(A, npic, s);
+    }
+    return launch_wide_steps<FV, FH, 64>(A, npic, s);
 }
 
 }  // namespace vc2b

@@ -6,6 +6,8 @@
 
 namespace vc2b {
 
+unsigned long long g_launch_count = 0;
+
 static int32_t subband_width(const vc2b_params *p, int level, int comp)
 {
     int32_t w = comp == 0 ? p->luma_width : p->color_diff_width;
@@ -225,6 +227,8 @@ using namespace vc2b;
 extern "C" {
 
 const char *vc2b_version(void) { return "vc2b200 0.1 (sm_100a)"; }
+
+int64_t vc2b_launch_count(void) { return (int64_t)__atomic_load_n(&vc2b::g_launch_count, __ATOMIC_RELAXED); }
 
 int vc2b_check_params(const vc2b_params *p)
 {

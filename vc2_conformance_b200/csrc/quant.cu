@@ -88,10 +88,18 @@ __device__ __forceinline__ int build_slice_bands(const DevParams &P, int comp, i
     int cnt = 0;
     if (lane < nb) {
         const Band &B = P.band[comp][lane];
-        int x1 = (int)(((long long)B.w * sx) / P.slices_x);
-        int x2 = (int)(((long long)B.w * (sx + 1)) / P.slices_x);
-        int y1 = (int)(((long long)B.h * sy) / P.slices_y);
-        int y2 = (int)(((long long)B.h * (sy + 1)) / P.slices_y);
+        int x1, x2, y1, y2;  // slice_left / right / top / bottom (pseudocode/slice_sizes.py:19-50)
+        if ((long long)B.w * (sx + 1) < 0x7fffffffLL && (long long)B.h * (sy + 1) < 0x7fffffffLL) {
+            x1 = (int)(((unsigned)B.w * (unsigned)sx) / (unsigned)P.slices_x);
+            x2 = (int)(((unsigned)B.w * (unsigned)(sx + 1)) / (unsigned)P.slices_x);
+            y1 = (int)(((unsigned)B.h * (unsigned)sy) / (unsigned)P.slices_y);
+            y2 = (int)(((unsigned)B.h * (unsigned)(sy + 1)) / (unsigned)P.slices_y);
+        } else {
+            x1 = (int)(((long long)B.w * sx) / P.slices_x);
+            x2 = (int)(((long long)B.w * (sx + 1)) / P.slices_x);
+            y1 = (int)(((long long)B.h * sy) / P.slices_y);
+            y2 = (int)(((long long)B.h * (sy + 1)) / P.slices_y);
+        }
         T.w[lane] = max(x2 - x1, 1);
         T.stride[lane] = B.w;
         T.base[lane] = B.off + y1 * B.w + x1;
@@ -110,17 +118,37 @@ __device__ __forceinline__ int build_slice_bands(const DevParams &P, int comp, i
     return __shfl_sync(0xffffffffu, pre, 31);
 }
 
+// Band and offset (inside the component) of coefficient j of the slice component: bisection over the
+// cumulative band sizes (branch-free, so that callers can keep several loads in flight).
+__device__ __forceinline__ int locate_coeff(const SliceBands &T, int nb, int j, int *band)
+{
+    int b = 0;
+#pragma unroll
+    for (int s = kMaxBands / 2; s > 0; s >>= 1) {
+        const int t = b + s;
+        if (t < nb && T.cum[t] <= j) b = t;  // largest b with cum[b] <= j: the (non-empty) band holding j
+    }
+    const int local = j - T.cum[b];
+    const int w = T.w[b];
+    int y, x;
+    if (local < (1 << 24)) {
+        y = (int)(((float)local + 0.5f) * (1.0f / (float)w));  // off by at most one, fixed below
+        x = local - y * w;
+        if (x < 0) { y--; x += w; }
+        else if (x >= w) { y++; x -= w; }
+    } else {
+        y = local / w;
+        x = local - y * w;
+    }
+    *band = b;
+    return T.base[b] + y * T.stride[b] + x;
+}
+
 // coefficient j (bitstream order, encoder/pictures.py:418-451) of the slice component
 __device__ __forceinline__ int32_t slice_coeff(const SliceBands &T, int nb, const int32_t *__restrict__ comp,
                                                int j, int *band)
 {
-    int b = 0;
-    while (b < nb - 1 && j >= T.cum[b + 1]) b++;
-    const int local = j - T.cum[b];
-    const int y = local / T.w[b];
-    const int x = local - y * T.w[b];
-    *band = b;
-    return comp[T.base[b] + y * T.stride[b] + x];
+    return comp[locate_coeff(T, nb, j, band)];
 }
 
 // signed_exp_golomb_length (bitstream/exp_golomb.py:28)
@@ -156,101 +184,157 @@ __device__ int slice_bits(const SliceBands &T, int nb, const int32_t *__restrict
 }
 
 // ---- slice staged in shared memory ------------------------------------------------------------
-// The bisection probes every coefficient of the slice ~8 times; gathering the slice once (in
-// bitstream order, with each coefficient's band) makes a probe a pure shared-memory pass.
+// The search probes every coefficient of the slice several times and the packer needs the values in
+// bitstream order; gathering the slice once (band by band: every band rectangle is a handful of
+// contiguous row segments) makes a probe a pure shared-memory pass.
 constexpr int kStageMax = 2048;  // coefficients (all components) of a slice that fit the staging buffer
 
+// Per-warp staging area carved out of dynamic shared memory: `cap` = the largest slice of the
+// parameter set (rounded up), so small slices leave room for more resident warps.
 struct SliceStage {
-    int32_t coef[kStageMax];     // bitstream order: Y, then C1, C2 (HQ) or C1/C2 interleaved (LD)
-    uint8_t band[kStageMax];
-    uint32_t qf[kMaxBands];      // per probe: quant_factor of each band (saturated)
-    uint32_t rcp[kMaxBands];     // floor((2^32-1) / qf)
+    uint2 *qtab;     // [kMaxBands] per probe and band: {min(qf, 2^30), floor(log2 of it)}
+    int32_t *coef;   // [cap] bitstream order: Y, then C1, C2 (HQ) or C1/C2 interleaved (LD); 4*|c|
+    uint8_t *band;   // [cap]
 };
 
-__device__ __forceinline__ void stage_slice(const DevParams &P, const SliceBands &TY, const SliceBands &TC,
-                                            const int32_t *__restrict__ pc, int ny, int nc, SliceStage &S, int lane)
+__host__ __device__ inline size_t slice_stage_bytes(int cap) { return kMaxBands * sizeof(uint2) + 5 * (size_t)cap; }
+
+__device__ __forceinline__ SliceStage slice_stage_at(unsigned char *base, int warp, int cap)
+{
+    unsigned char *p = base + warp * slice_stage_bytes(cap);
+    SliceStage S;
+    S.qtab = reinterpret_cast<uint2 *>(p);
+    S.coef = reinterpret_cast<int32_t *>(p + kMaxBands * sizeof(uint2));
+    S.band = p + kMaxBands * sizeof(uint2) + 4 * (size_t)cap;
+    return S;
+}
+
+// Gathers the slice rectangle of one component into dst[j * step] (step 2: C1/C2 interleaved, ld_slice),
+// eight independent loads per lane in flight.  ABS4: store 4*|c| (saturated at 2^32-1 for |c| >= 2^30);
+// returns the lane's largest |c|.
+template <bool ABS4>
+__device__ __forceinline__ uint32_t stage_component(const SliceBands &T, int nb, const int32_t *__restrict__ comp,
+                                                    int n, int32_t *dst, uint8_t *dband, int step, int lane)
+{
+    constexpr int U = 8;
+    uint32_t mx = 0;
+    for (int j0 = 0; j0 < n; j0 += 32 * U) {
+        int32_t v[U];
+        int bb[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int j = j0 + 32 * u + lane;
+            v[u] = 0;
+            bb[u] = 0;
+            if (j < n) v[u] = __ldg(comp + locate_coeff(T, nb, j, &bb[u]));
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int j = j0 + 32 * u + lane;
+            if (j < n) {
+                const int32_t c = v[u];
+                if (ABS4) {
+                    const uint32_t m = c < 0 ? (uint32_t)(-(long long)c) : (uint32_t)c;
+                    mx = max(mx, m);
+                    dst[j * step] = (int32_t)(m >= 0x40000000u ? 0xffffffffu : 4u * m);
+                } else {
+                    dst[j * step] = c;
+                }
+                dband[j * step] = (uint8_t)bb[u];
+            }
+        }
+    }
+    return mx;
+}
+
+template <bool ABS4>
+__device__ __forceinline__ uint32_t stage_slice(const DevParams &P, const SliceBands &TY, const SliceBands &TC,
+                                                const int32_t *__restrict__ pc, int ny, int nc, const SliceStage &S, int lane)
 {
     const int32_t *cy = pc + P.comp_off[0], *c1 = pc + P.comp_off[1], *c2 = pc + P.comp_off[2];
-    for (int j = lane; j < ny; j += 32) {
-        int b;
-        S.coef[j] = slice_coeff(TY, P.nb, cy, j, &b);
-        S.band[j] = (uint8_t)b;
-    }
+    uint32_t mx = stage_component<ABS4>(TY, P.nb, cy, ny, S.coef, S.band, 1, lane);
     if (P.is_ld) {
-        for (int j = lane; j < 2 * nc; j += 32) {
-            int b;
-            S.coef[ny + j] = slice_coeff(TC, P.nb, (j & 1) ? c2 : c1, j >> 1, &b);
-            S.band[ny + j] = (uint8_t)b;
-        }
+        mx = max(mx, stage_component<ABS4>(TC, P.nb, c1, nc, S.coef + ny, S.band + ny, 2, lane));
+        mx = max(mx, stage_component<ABS4>(TC, P.nb, c2, nc, S.coef + ny + 1, S.band + ny + 1, 2, lane));
     } else {
-        for (int j = lane; j < nc; j += 32) {
-            int b;
-            S.coef[ny + j] = slice_coeff(TC, P.nb, c1, j, &b);
-            S.band[ny + j] = (uint8_t)b;
-            S.coef[ny + nc + j] = slice_coeff(TC, P.nb, c2, j, &b);
-            S.band[ny + nc + j] = (uint8_t)b;
-        }
+        mx = max(mx, stage_component<ABS4>(TC, P.nb, c1, nc, S.coef + ny, S.band + ny, 1, lane));
+        mx = max(mx, stage_component<ABS4>(TC, P.nb, c2, nc, S.coef + ny + nc, S.band + ny + nc, 1, lane));
+    }
+    __syncwarp();
+    return __reduce_max_sync(0xffffffffu, mx);
+}
+
+// ---- quantiser search probe -------------------------------------------------------------------
+// The coded length of a value only needs k = floor(log2(q + 1)), q = floor(n / qf), n = 4|c|
+// (signed_exp_golomb_length: 1 bit for q = 0, else 2k + 2).  q + 1 = floor((n + qf) / qf), so with
+// x = n + qf and d = floor(log2 x) - floor(log2 qf):  k = d if (qf << d) <= x, else d - 1 -- no
+// division.  Valid for n < 2^30 with qf clamped to 2^30 (a larger factor quantises every such n to
+// zero, and so does 2^30); slices holding larger magnitudes take the generic path.
+constexpr uint32_t kFastMagLimit = 0x10000000u;  // |c| < 2^28
+
+__device__ __forceinline__ void stage_search_quantisers(const SliceBands &T, int nb, int qindex, const SliceStage &S, int lane)
+{
+    __syncwarp();
+    if (lane < nb) {
+        const uint64_t qf = quant_factor_u64(max(qindex - T.qm[lane], 0));
+        const uint32_t y = qf > 0x40000000ull ? 0x40000000u : (uint32_t)qf;
+        S.qtab[lane] = make_uint2(y, 31 - __clz(y));
     }
     __syncwarp();
 }
 
-__device__ __forceinline__ void stage_quantisers(const SliceBands &T, int nb, int qindex, SliceStage &S, int lane)
+// calculate_coeffs_bits (encoder/pictures.py:217) of the staged block [j0, j0 + cnt) at the staged quantisers
+__device__ __forceinline__ int staged_block_bits(const SliceStage &S, int j0, int cnt, int lane)
+{
+    int acc = 0, last = -1;  // acc = sum of (2k + [k > 0])
+#pragma unroll 4
+    for (int j = lane; j < cnt; j += 32) {
+        const uint32_t n = (uint32_t)S.coef[j0 + j];
+        const uint2 t = S.qtab[S.band[j0 + j]];
+        const uint32_t x = n + t.x;
+        const int d = (31 - __clz(x)) - (int)t.y;
+        const int k = d - (((t.x << d) > x) ? 1 : 0);
+        acc += 2 * k;
+        if (k > 0) { acc++; last = j; }
+    }
+    acc = __reduce_add_sync(0xffffffffu, acc);
+    last = __reduce_max_sync(0xffffffffu, last);
+    // sum of lengths = acc + cnt; trailing zeros (cnt - 1 - last) are free
+    return acc + last + 1;
+}
+
+// ---- packer quantisation ----------------------------------------------------------------------
+__device__ __forceinline__ void stage_pack_quantisers(const SliceBands &T, int nb, int qindex, uint2 *qtab, int lane)
 {
     __syncwarp();
     if (lane < nb) {
         const uint64_t qf = quant_factor_u64(max(qindex - T.qm[lane], 0));
         const uint32_t q32 = qf > 0xfffffffeull ? 0xffffffffu : (uint32_t)qf;
-        S.qf[lane] = q32;
-        S.rcp[lane] = 0xffffffffu / q32;
+        qtab[lane] = make_uint2(q32, 0xffffffffu / q32);
     }
     __syncwarp();
 }
 
 // forward_quant magnitude with the staged reciprocal: exact floor(4m / qf)
-__device__ __forceinline__ uint32_t staged_quant_mag(const SliceStage &S, int b, int32_t c)
+__device__ __forceinline__ uint32_t staged_quant_mag(const uint2 *qtab, int b, int32_t c)
 {
     const uint32_t m = c < 0 ? (uint32_t)(-(long long)c) : (uint32_t)c;
-    const uint32_t qf = S.qf[b];
+    const uint2 t = qtab[b];
+    const uint32_t qf = t.x;
     if (m >= 0x40000000u) return qf == 0xffffffffu ? 0u : (uint32_t)((4ull * m) / qf);  // 4m overflows 32 bits
     if (qf == 0xffffffffu) return 0u;  // quant_factor >= 2^32 > 4m
     const uint32_t n = 4u * m;
-    uint32_t q = __umulhi(n, S.rcp[b]);
+    uint32_t q = __umulhi(n, t.y);
     uint32_t r = n - q * qf;
     while (r >= qf) { q++; r -= qf; }  // at most two corrections
     return q;
-}
-
-// bits of the three blocks (Y | C1 | C2, or Y | C for LD) of the staged slice at `qindex`
-__device__ __forceinline__ void staged_bits(const SliceStage &S, int n0, int n1, int n2, int lane, int &b0, int &b1,
-                                            int &b2)
-{
-    int sum0 = 0, sum1 = 0, sum2 = 0, last0 = -1, last1 = -1, last2 = -1;
-    const int e0 = n0, e1 = n0 + n1, e2 = n0 + n1 + n2;
-    for (int j = lane; j < e2; j += 32) {
-        const uint32_t q = staged_quant_mag(S, S.band[j], S.coef[j]);
-        const int len = sint_length(q);
-        if (j < e0) { sum0 += len; if (q) last0 = j; }
-        else if (j < e1) { sum1 += len; if (q) last1 = j - e0; }
-        else { sum2 += len; if (q) last2 = j - e1; }
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        sum0 += __shfl_xor_sync(0xffffffffu, sum0, d);
-        sum1 += __shfl_xor_sync(0xffffffffu, sum1, d);
-        sum2 += __shfl_xor_sync(0xffffffffu, sum2, d);
-        last0 = max(last0, __shfl_xor_sync(0xffffffffu, last0, d));
-        last1 = max(last1, __shfl_xor_sync(0xffffffffu, last1, d));
-        last2 = max(last2, __shfl_xor_sync(0xffffffffu, last2, d));
-    }
-    b0 = sum0 - (n0 - 1 - last0);  // trailing zeros are free (calculate_coeffs_bits :217)
-    b1 = sum1 - (n1 - 1 - last1);
-    b2 = n2 > 0 ? sum2 - (n2 - 1 - last2) : 0;
 }
 
 struct FitArgs {
     long long total_coeff_bytes;  // HQ: picture_bytes - 4*slices
     int minimum_qindex;
     int max_qm;
+    int stage_cap;                // coefficients the per-warp staging area holds (quantize_fit_kernel)
 };
 
 __device__ __forceinline__ long long hq_total_length(const DevParams &P, const FitArgs &F, long long n)
@@ -270,7 +354,7 @@ quantize_fit_kernel(DevParams P, FitArgs F, const int32_t *__restrict__ coeffs, 
                     int32_t *__restrict__ qindex_out, int32_t *__restrict__ bits_out)
 {
     __shared__ SliceBands tabs[kQWarps][2];
-    __shared__ SliceStage stages[kQWarps];
+    extern __shared__ __align__(16) unsigned char stage_mem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nslices = P.slices_x * P.slices_y;
     const long long gw = (long long)blockIdx.x * kQWarps + warp;
@@ -281,11 +365,12 @@ quantize_fit_kernel(DevParams P, FitArgs F, const int32_t *__restrict__ coeffs, 
     const int32_t *pc = coeffs + (size_t)pic * P.pic_coeffs;
     SliceBands &TY = tabs[warp][0];
     SliceBands &TC = tabs[warp][1];
-    SliceStage &S = stages[warp];
+    const SliceStage S = slice_stage_at(stage_mem, warp, F.stage_cap);
     const int ny = build_slice_bands(P, 0, sx, sy, TY, lane);
     const int nc = build_slice_bands(P, 1, sx, sy, TC, lane);
-    const bool staged = (ny + 2 * nc) <= kStageMax;
-    if (staged) stage_slice(P, TY, TC, pc, ny, nc, S, lane);
+    // fast path: slice staged as 4|c| in shared memory, every magnitude below kFastMagLimit
+    bool staged = (ny + 2 * nc) <= F.stage_cap;
+    if (staged) staged = stage_slice<true>(P, TY, TC, pc, ny, nc, S, lane) < kFastMagLimit;
 
     long long target, align;
     if (P.is_ld) {
@@ -297,31 +382,40 @@ quantize_fit_kernel(DevParams P, FitArgs F, const int32_t *__restrict__ coeffs, 
         align = 8LL * P.slice_size_scaler;
         target = align * hq_total_length(P, F, n);
     }
+    const int ialign = (int)align;
 
-    int by = 0, bc1 = 0, bc2 = 0;
+    int by = 0, bc1 = 0, bc2 = 0;   // bits of the last probe
+    int ok_q = -1, oy = 0, o1 = 0, o2 = 0;  // last probe that fitted
     auto fits = [&](int q) -> bool {
         long long total;
         if (staged) {  // quant matrices are per band, identical for the three components
-            stage_quantisers(TY, P.nb, q, S, lane);
+            stage_search_quantisers(TY, P.nb, q, S, lane);
+            by = staged_block_bits(S, 0, ny, lane);
             if (P.is_ld) {
-                staged_bits(S, ny, 2 * nc, 0, lane, by, bc1, bc2);
-                return (long long)by + bc1 <= target;
+                bc1 = staged_block_bits(S, ny, 2 * nc, lane);
+                bc2 = 0;
+                total = (long long)by + bc1;
+            } else {
+                bc1 = staged_block_bits(S, ny, nc, lane);
+                bc2 = staged_block_bits(S, ny + nc, nc, lane);
+                total = (long long)((by + ialign - 1) / ialign + (bc1 + ialign - 1) / ialign + (bc2 + ialign - 1) / ialign) *
+                        ialign;
             }
-            staged_bits(S, ny, nc, nc, lane, by, bc1, bc2);
-            total = ((by + align - 1) / align + (bc1 + align - 1) / align + (bc2 + align - 1) / align) * align;
-            return total <= target;
-        }
-        by = slice_bits<false>(TY, P.nb, pc + P.comp_off[0], nullptr, ny, q, lane);
-        if (P.is_ld) {
-            bc1 = slice_bits<true>(TC, P.nb, pc + P.comp_off[1], pc + P.comp_off[2], 2 * nc, q, lane);
-            bc2 = 0;
-            total = (long long)by + bc1;
         } else {
-            bc1 = slice_bits<false>(TC, P.nb, pc + P.comp_off[1], nullptr, nc, q, lane);
-            bc2 = slice_bits<false>(TC, P.nb, pc + P.comp_off[2], nullptr, nc, q, lane);
-            total = ((by + align - 1) / align + (bc1 + align - 1) / align + (bc2 + align - 1) / align) * align;
+            by = slice_bits<false>(TY, P.nb, pc + P.comp_off[0], nullptr, ny, q, lane);
+            if (P.is_ld) {
+                bc1 = slice_bits<true>(TC, P.nb, pc + P.comp_off[1], pc + P.comp_off[2], 2 * nc, q, lane);
+                bc2 = 0;
+                total = (long long)by + bc1;
+            } else {
+                bc1 = slice_bits<false>(TC, P.nb, pc + P.comp_off[1], nullptr, nc, q, lane);
+                bc2 = slice_bits<false>(TC, P.nb, pc + P.comp_off[2], nullptr, nc, q, lane);
+                total = ((by + align - 1) / align + (bc1 + align - 1) / align + (bc2 + align - 1) / align) * align;
+            }
         }
-        return total <= target;
+        const bool ok = total <= target;
+        if (ok) { ok_q = q; oy = by; o1 = bc1; o2 = bc2; }
+        return ok;
     };
 
     // The total is non-increasing in qindex (|forward_quant| is non-increasing in the quantiser),
@@ -354,7 +448,8 @@ quantize_fit_kernel(DevParams P, FitArgs F, const int32_t *__restrict__ coeffs, 
         }
         if (lane == 0) g_qindex_hint[pic & (kHintSlots - 1)] = lo;
     }
-    fits(lo);
+    if (ok_q == lo) { by = oy; bc1 = o1; bc2 = o2; }  // the answer is the last probe that fitted
+    else fits(lo);
     if (lane == 0) {
         qindex_out[gw] = lo;
         if (bits_out) {
@@ -423,22 +518,29 @@ __device__ __forceinline__ unsigned long long sint_code(int32_t v, int *len)
 }
 
 // Packs one bounded block: values in bitstream order at absolute bit `start`, block end `end`.
+// The coefficients of the next 32 values are fetched while the current ones are coded.
 template <bool INTERLEAVED>
 __device__ void pack_block(const SliceBands &T, int nb, const int32_t *__restrict__ c1,
-                           const int32_t *__restrict__ c2, int ncoef, int qindex, uint32_t *__restrict__ out32,
+                           const int32_t *__restrict__ c2, int ncoef, const uint2 *qtab, uint32_t *__restrict__ out32,
                            long long start, long long end, int lane)
 {
+    auto fetch = [&](int idx, int *band) -> int32_t {
+        if (idx >= ncoef) { *band = 0; return 0; }
+        const int j = INTERLEAVED ? (idx >> 1) : idx;
+        return __ldg(((INTERLEAVED && (idx & 1)) ? c2 : c1) + locate_coeff(T, nb, j, band));
+    };
     long long pos = start;
+    int bn;
+    int32_t cn = fetch(lane, &bn);
     for (int i0 = 0; i0 < ncoef && pos < end; i0 += 32) {
         const int idx = i0 + lane;
+        const int32_t c = cn;
+        const int b = bn;
+        cn = fetch(idx + 32, &bn);
         int len = 0;
         unsigned long long code = 0;
         if (idx < ncoef) {
-            const int j = INTERLEAVED ? (idx >> 1) : idx;
-            int b;
-            const int32_t c = slice_coeff(T, nb, (INTERLEAVED && (idx & 1)) ? c2 : c1, j, &b);
-            const uint32_t m = c < 0 ? (uint32_t)(-(long long)c) : (uint32_t)c;
-            const uint32_t q = forward_quant_mag(m, quant_factor_u64(max(qindex - T.qm[b], 0)));
+            const uint32_t q = staged_quant_mag(qtab, b, c);
             code = sint_code(c < 0 ? -(int32_t)q : (int32_t)q, &len);
         }
         int pre = len;
@@ -458,6 +560,7 @@ pack_slices_kernel(DevParams P, FitArgs F, const int32_t *__restrict__ coeffs, i
                    uint8_t *__restrict__ out, long long out_stride)
 {
     __shared__ SliceBands tabs[kQWarps][2];
+    __shared__ uint2 qtabs[kQWarps][kMaxBands];  // {qf saturated to 2^32-1, floor((2^32-1) / qf)} per band
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nslices = P.slices_x * P.slices_y;
     const long long gw = (long long)blockIdx.x * kQWarps + warp;
@@ -468,9 +571,11 @@ pack_slices_kernel(DevParams P, FitArgs F, const int32_t *__restrict__ coeffs, i
     const int32_t *pc = coeffs + (size_t)pic * P.pic_coeffs;
     SliceBands &TY = tabs[warp][0];
     SliceBands &TC = tabs[warp][1];
+    const uint2 *qtab = qtabs[warp];
     const int ny = build_slice_bands(P, 0, sx, sy, TY, lane);
     const int nc = build_slice_bands(P, 1, sx, sy, TC, lane);
     const int qindex = qindex_in[gw];
+    stage_pack_quantisers(TY, P.nb, qindex, qtabs[warp], lane);  // quant matrices are identical for the components
     uint32_t *out32 = reinterpret_cast<uint32_t *>(out);  // out is 4-byte aligned; positions absolute
     const long long pic_bit0 = 8 * (long long)pic * out_stride;
 
@@ -487,9 +592,9 @@ pack_slices_kernel(DevParams P, FitArgs F, const int32_t *__restrict__ coeffs, i
             put_bits(out32, pos + 7, (unsigned long long)y_len, length_bits, end);
         }
         pos += 7 + length_bits;
-        pack_block<false>(TY, P.nb, pc + P.comp_off[0], nullptr, ny, qindex, out32, pos, pos + y_len, lane);
+        pack_block<false>(TY, P.nb, pc + P.comp_off[0], nullptr, ny, qtab, out32, pos, pos + y_len, lane);
         pos += y_len;
-        pack_block<true>(TC, P.nb, pc + P.comp_off[1], pc + P.comp_off[2], 2 * nc, qindex, out32, pos, end, lane);
+        pack_block<true>(TC, P.nb, pc + P.comp_off[1], pc + P.comp_off[2], 2 * nc, qtab, out32, pos, end, lane);
     } else {
         // hq_slice (bitstream/vc2.py:798): prefix bytes (zero), qindex, then per component a
         // length byte and a bounded block of 8*scaler*length bits (make_hq_slice :456)
@@ -508,15 +613,15 @@ pack_slices_kernel(DevParams P, FitArgs F, const int32_t *__restrict__ coeffs, i
             put_bits(out32, pos + 8, (unsigned long long)ly, 8, big);
         }
         pos += 16;
-        pack_block<false>(TY, P.nb, pc + P.comp_off[0], nullptr, ny, qindex, out32, pos, pos + align * ly, lane);
+        pack_block<false>(TY, P.nb, pc + P.comp_off[0], nullptr, ny, qtab, out32, pos, pos + align * ly, lane);
         pos += align * ly;
         if (lane == 0) put_bits(out32, pos, (unsigned long long)l1, 8, big);
         pos += 8;
-        pack_block<false>(TC, P.nb, pc + P.comp_off[1], nullptr, nc, qindex, out32, pos, pos + align * l1, lane);
+        pack_block<false>(TC, P.nb, pc + P.comp_off[1], nullptr, nc, qtab, out32, pos, pos + align * l1, lane);
         pos += align * l1;
         if (lane == 0) put_bits(out32, pos, (unsigned long long)l2, 8, big);
         pos += 8;
-        pack_block<false>(TC, P.nb, pc + P.comp_off[2], nullptr, nc, qindex, out32, pos, pos + align * l2, lane);
+        pack_block<false>(TC, P.nb, pc + P.comp_off[2], nullptr, nc, qtab, out32, pos, pos + align * l2, lane);
     }
 }
 
@@ -583,8 +688,16 @@ int vc2b_quantize_to_fit(const vc2b_params *p, const int32_t *d_coeffs, int npic
     }
     F.minimum_qindex = minimum_qindex < 0 ? 0 : minimum_qindex;
     F.max_qm = max_qm(P);
+    // staging area: the largest slice (every band rectangle is at most ceil(w / slices_x) x ceil(h / slices_y))
+    long long cap = 0;
+    for (int c = 0; c < 3; c++)
+        for (int b = 0; b < P.nb; b++)
+            cap += (long long)((P.band[c][b].w + P.slices_x - 1) / P.slices_x) *
+                   ((P.band[c][b].h + P.slices_y - 1) / P.slices_y);
+    F.stage_cap = cap <= kStageMax ? (int)((cap + 15) & ~15LL) : 16;  // larger slices are searched unstaged
+    const size_t smem = kQWarps * slice_stage_bytes(F.stage_cap);
     const long long warps = npictures * nslices;
-    quantize_fit_kernel<<<(unsigned)((warps + kQWarps - 1) / kQWarps), kQWarps * 32, 0, (cudaStream_t)stream>>>(
+    quantize_fit_kernel<<<(unsigned)((warps + kQWarps - 1) / kQWarps), kQWarps * 32, smem, (cudaStream_t)stream>>>(
         P, F, d_coeffs, npictures, d_qindex, d_slice_bits);
     VC2B_CHECK_LAUNCH();
     return 0;
@@ -624,6 +737,7 @@ int vc2b_pack_slices(const vc2b_params *p, const int32_t *d_coeffs, int npicture
     F.total_coeff_bytes = picture_bytes - 4 * nslices;
     F.minimum_qindex = 0;
     F.max_qm = max_qm(P);
+    F.stage_cap = 0;
     cudaStream_t s = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(d_out, 0, (size_t)out_stride * npictures, s);
     if (e != cudaSuccess) return (int)e;

@@ -720,13 +720,10 @@ namespace vc2b {
 
 // ---------------------------------------------------------------------------
 // DC prediction (decoder/transform_data_syntax.py:63 dc_prediction and its inverse
-// encoder/pictures.py:202 apply_dc_prediction).  One CTA per (picture, component); thread y
-// owns row y of a strip of rows and runs skewed by one column per row, so the three
-// neighbours (left: own register; up and up-left: the row above, two steps earlier) are
-// always final.  mean(a,b,c) = (a+b+c+1)//3 with floor division (pseudocode/vc2_math.py:57).
+// encoder/pictures.py:202 apply_dc_prediction).  One CTA per (picture, component).
+// mean(a,b,c) = (a+b+c+1)//3 with floor division (pseudocode/vc2_math.py:57).
 // ---------------------------------------------------------------------------
 constexpr int kDcThreads = 256;
-constexpr int kDcRing = 8;   // cp.async slots per thread (power of two)
 
 __device__ __forceinline__ long long floordiv3(long long v)
 {
@@ -753,11 +750,190 @@ __device__ __forceinline__ int narrow_or_flag(long long v, int *maxabs)
     return (int)v;
 }
 
-__global__ void __launch_bounds__(kDcThreads)
-dc_prediction_kernel(DevParams P, int32_t *__restrict__ coeffs, int inverse, int32_t *__restrict__ status)
+// ---- decoder direction: warp-pipelined wavefront ---------------------------------------------------
+// out[y][x] = in[y][x] + mean(out[y][x-1], out[y-1][x-1], out[y-1][x]) is a true 2-D recurrence; what is
+// parallel is the anti-diagonal.  A warp owns 32 consecutive rows, lane l = row, and runs skewed: at
+// step s lane l handles column group s - l (four columns), so the group of the row above was finished
+// by lane l-1 one step earlier and arrives by ONE warp shuffle per value -- no shared memory, no block
+// barrier on the chain.  The warps of a CTA are pipelined down the band: lane 0 of warp b reads the row
+// above (the last row of warp b-1) back from global memory, eight groups ahead, once warp b-1 has
+// published (fence + a shared progress word) that it is written; in steady state the producer is 31
+// steps ahead and nobody spins.  Own rows are prefetched eight steps ahead into a register ring.
+constexpr int kDcWarps = 8;      // rows per pass = 32 * kDcWarps
+constexpr int kDcAhead = 8;      // groups prefetched ahead (register ring; loop unrolled by it)
+
+struct DcLane {
+    int left, upleft, maxabs;
+};
+
+// four columns of one row: `in` the residues, `uv` the finished row above; returns the finished values
+__device__ __forceinline__ int4 dc_group(DcLane &L, const int4 cur, const int4 upv, int x0, int y, int w)
 {
-    __shared__ int4 up[2][kDcThreads + 1];
-    __shared__ int4 stage[kDcRing][kDcThreads];
+    const int in[4] = {cur.x, cur.y, cur.z, cur.w};
+    const int uv[4] = {upv.x, upv.y, upv.z, upv.w};
+    int o[4];
+    // The recurrence is a dependent chain through `left`, so it is kept short: with all operands within
+    // +-2^29 (any real stream) the mean is one biased multiply-high in 32 bits, the edge cases are
+    // selects, and the range checks are gathered into one flag.  If the flag fails the group is redone
+    // exactly in 64 bits.
+    bool ok = dc_small(L.left) && dc_small(L.upleft);
+    {
+        int l = L.left, ul = L.upleft;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int x = x0 + i;
+            const bool interior = (x > 0) && (y > 0);
+            const unsigned t1 = (unsigned)ul + (unsigned)uv[i] + 0xC0000001u;  // + 1 + 3*2^30
+            const unsigned inb = (unsigned)in[i] - (1u << 30);
+            ok = ok && dc_small(uv[i]) && dc_small(in[i]);
+            const int q = (int)((__umulhi((unsigned)l + t1, 0xAAAAAAABu) >> 1) + inb);
+            const int e = (int)((unsigned)in[i] + (unsigned)(x > 0 ? l : uv[i]));  // first row: left; first column: up
+            const int v = interior ? q : e;
+            ok = ok && dc_small(v);
+            o[i] = v;
+            l = v;
+            ul = uv[i];
+        }
+    }
+    if (ok) {
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (x0 + i < w) L.maxabs = max(L.maxabs, o[i] < 0 ? -o[i] : o[i]);
+        L.left = o[3];
+        L.upleft = uv[3];
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int x = x0 + i;
+            long long pred;
+            if (x > 0 && y > 0) pred = floordiv3((long long)L.left + L.upleft + uv[i] + 1);
+            else if (x > 0) pred = L.left;
+            else if (y > 0) pred = uv[i];
+            else pred = 0;
+            o[i] = (x < w) ? narrow_or_flag((long long)in[i] + pred, &L.maxabs) : 0;
+            L.left = o[i];
+            L.upleft = uv[i];
+        }
+    }
+    return make_int4(o[0], o[1], o[2], o[3]);
+}
+
+__global__ void __launch_bounds__(kDcWarps * 32)
+dc_prediction_fwd_kernel(DevParams P, int32_t *__restrict__ coeffs, int32_t *__restrict__ status)
+{
+    __shared__ volatile int progress[kDcWarps];  // groups of the warp's last row that are final in global memory
+    const int pic = blockIdx.x / 3, comp = blockIdx.x % 3;
+    const Band &B = P.band[comp][0];
+    const int w = B.w, h = B.h;
+    int32_t *band = coeffs + (size_t)pic * P.pic_coeffs + P.comp_off[comp] + B.off;
+    const int lane = threadIdx.x & 31, wb = threadIdx.x >> 5;
+    const int ngroups = (w + 3) >> 2;
+    const bool vec = (w & 3) == 0 && ((reinterpret_cast<uintptr_t>(band) & 15) == 0);
+    DcLane L;
+    L.maxabs = 0;
+
+    // Rows are read 16 bytes at a time with a row stride between neighbouring lanes, which is a poor
+    // DRAM pattern: pull the band into L2 first with one coalesced sweep of prefetches.
+    {
+        const char *b0 = reinterpret_cast<const char *>(band);
+        const size_t nbytes = (size_t)w * h * sizeof(int32_t);
+        for (size_t off = (size_t)threadIdx.x * 128; off < nbytes; off += (size_t)kDcWarps * 32 * 128)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(b0 + off));
+    }
+
+    auto load_group = [&](const int32_t *row, int g) -> int4 {  // group g of a row (L2; never L1: rows above are
+        int4 v = make_int4(0, 0, 0, 0);                          // written by another warp)
+        if (g < 0 || g >= ngroups) return v;
+        if (vec) return __ldcg(reinterpret_cast<const int4 *>(row) + g);
+        const int x = 4 * g;
+        v.x = __ldcg(row + x);
+        if (x + 1 < w) v.y = __ldcg(row + x + 1);
+        if (x + 2 < w) v.z = __ldcg(row + x + 2);
+        if (x + 3 < w) v.w = __ldcg(row + x + 3);
+        return v;
+    };
+
+    for (int y0 = 0; y0 < h; y0 += 32 * kDcWarps) {
+        if (threadIdx.x < kDcWarps) progress[threadIdx.x] = 0;
+        __syncthreads();
+        const int yw = y0 + 32 * wb;          // first row of this warp
+        const int y = yw + lane;
+        if (yw < h) {
+            const bool row_ok = y < h;
+            int32_t *row = band + (size_t)(row_ok ? y : h - 1) * w;
+            const int32_t *above = band + (size_t)(yw > 0 ? yw - 1 : 0) * w;   // lane 0's row above
+            const bool has_above = yw > 0;
+            const bool wait_above = wb > 0;    // written by warp wb-1 of this pass (else: final since the last pass)
+            // lane 0 may read group g of the row above once progress[wb-1] > g
+            auto wait_for = [&](int g) {
+                if (!wait_above) return;
+                const int need = min(g, ngroups - 1) + 1;
+                while (progress[wb - 1] < need) { }
+                __threadfence_block();
+            };
+            L.left = 0;
+            L.upleft = 0;
+            int4 ring[kDcAhead], upring[kDcAhead];
+            wait_for(kDcAhead - 1);
+#pragma unroll
+            for (int u = 0; u < kDcAhead; u++) {
+                ring[u] = row_ok ? load_group(row, u - lane) : make_int4(0, 0, 0, 0);
+                upring[u] = (lane == 0 && has_above) ? load_group(above, u) : make_int4(0, 0, 0, 0);
+            }
+            int4 prev = make_int4(0, 0, 0, 0);   // this lane's output of the previous step
+            const int nsteps = ngroups + 31;
+            for (int s0 = 0; s0 < nsteps; s0 += kDcAhead) {
+                wait_for(s0 + 2 * kDcAhead - 1);  // the groups refilled during this block
+#pragma unroll
+                for (int u = 0; u < kDcAhead; u++) {
+                    const int s = s0 + u;
+                    const int g = s - lane;
+                    int4 upv;
+                    upv.x = __shfl_up_sync(0xffffffffu, prev.x, 1);
+                    upv.y = __shfl_up_sync(0xffffffffu, prev.y, 1);
+                    upv.z = __shfl_up_sync(0xffffffffu, prev.z, 1);
+                    upv.w = __shfl_up_sync(0xffffffffu, prev.w, 1);
+                    if (lane == 0) upv = upring[u];
+                    const int4 cur = ring[u];
+                    // refill the slots with the groups of step s + kDcAhead
+                    ring[u] = row_ok ? load_group(row, g + kDcAhead) : make_int4(0, 0, 0, 0);
+                    if (lane == 0 && has_above) upring[u] = load_group(above, s + kDcAhead);
+                    int4 out = make_int4(0, 0, 0, 0);
+                    const bool active = row_ok && g >= 0 && g < ngroups;
+                    if (active) {
+                        const int x0 = 4 * g;
+                        out = dc_group(L, cur, upv, x0, y, w);
+                        if (vec) {
+                            *reinterpret_cast<int4 *>(row + x0) = out;
+                        } else {
+                            row[x0] = out.x;
+                            if (x0 + 1 < w) row[x0 + 1] = out.y;
+                            if (x0 + 2 < w) row[x0 + 2] = out.z;
+                            if (x0 + 3 < w) row[x0 + 3] = out.w;
+                        }
+                        if (lane == 31) {  // the next warp's row above: publish
+                            __threadfence_block();
+                            progress[wb] = g + 1;
+                        }
+                    }
+                    prev = out;
+                }
+            }
+        }
+        __threadfence_block();
+        __syncthreads();   // rows of this pass are final for the next one
+    }
+    if (status) {
+        int maxabs = L.maxabs;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) maxabs = max(maxabs, __shfl_xor_sync(0xffffffffu, maxabs, d));
+        if (lane == 0 && maxabs) atomicMax(&status[4 * pic + 3], maxabs);
+    }
+}
+
+__global__ void __launch_bounds__(kDcThreads)
+dc_prediction_inverse_kernel(DevParams P, int32_t *__restrict__ coeffs, int32_t *__restrict__ status)
+{
     const int pic = blockIdx.x / 3, comp = blockIdx.x % 3;
     const Band &B = P.band[comp][0];
     const int w = B.w, h = B.h;
@@ -765,168 +941,34 @@ dc_prediction_kernel(DevParams P, int32_t *__restrict__ coeffs, int inverse, int
     const int t = threadIdx.x;
     int maxabs = 0;  // running max |coefficient| of this thread
 
-    if (!inverse) {
-        // Forward recurrence.  Thread t owns row y0+t of a strip of rows and handles FOUR columns per
-        // step, one step behind the row above, so up / up-left are final when they are needed: they
-        // travel through shared memory (double-buffered int4), left stays in a register.  Each row
-        // is read with 16-byte loads issued two steps early and written with 16-byte stores; nothing
-        // written here is read back from global memory within a strip.
-        const int ngroups = (w + 3) >> 2;
-        const bool vec = (w & 3) == 0 && ((reinterpret_cast<uintptr_t>(band) & 15) == 0);
-        // Rows are read 16 bytes at a time with a row stride between neighbouring threads, which is a
-        // poor DRAM pattern: pull the band into L2 first with one coalesced sweep of prefetches.
-        {
-            const char *b0 = reinterpret_cast<const char *>(band);
-            const size_t nbytes = (size_t)w * h * sizeof(int32_t);
-            for (size_t off = (size_t)t * 128; off < nbytes; off += (size_t)kDcThreads * 128)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(b0 + off));
-        }
-        for (int y0 = 0; y0 < h; y0 += kDcThreads) {
-            const int y = y0 + t;
-            const bool active = y < h;
-            const int rows = min(kDcThreads, h - y0);
-            int32_t *row = band + (size_t)y * w;
-            // Each thread streams its row through a private ring of shared-memory slots filled by
-            // cp.async seven steps ahead: register prefetches do not survive the per-step barrier
-            // (measured: 283 us with them against 100 us without any load, 64 fields), async copies do.
-            auto issue = [&](int g) {
-                if (vec && active && g >= 0 && g < ngroups) {
-                    const unsigned sa = (unsigned)__cvta_generic_to_shared(&stage[g & (kDcRing - 1)][t]);
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(row + 4 * g) : "memory");
-                }
-                asm volatile("cp.async.commit_group;" ::: "memory");
-            };
-            auto load4 = [&](int g) -> int4 {   // group g of this row (g in range)
-                int4 v = make_int4(0, 0, 0, 0);
-                if (vec) {
-                    v = stage[g & (kDcRing - 1)][t];
-                } else {
-                    const int x = 4 * g;
-                    v.x = row[x];
-                    if (x + 1 < w) v.y = row[x + 1];
-                    if (x + 2 < w) v.z = row[x + 2];
-                    if (x + 3 < w) v.w = row[x + 3];
-                }
-                return v;
-            };
-            for (int k = 0; k < kDcRing - 1; k++) issue(k - t);
-            int left = 0;     // band[y][x-1] (final)
-            int upleft = 0;   // band[y-1][x-1] (final)
-            const int nsteps = ngroups + rows - 1;
-            for (int step = 0; step < nsteps; step++) {
-                const int g = step - t;
-                int4 out = make_int4(0, 0, 0, 0);
-                issue(g + kDcRing - 1);
-                asm volatile("cp.async.wait_group %0;" ::"n"(kDcRing - 1) : "memory");
-                if (active && g >= 0 && g < ngroups) {
-                    const int x0 = 4 * g;
-                    const int4 cur = load4(g);
-                    int4 upv = make_int4(0, 0, 0, 0);
-                    if (y > 0) {
-                        if (t == 0) {  // first row of a later strip: the row above is final in global memory
-                            const int32_t *prow = row - w;
-                            upv.x = prow[x0];
-                            if (x0 + 1 < w) upv.y = prow[x0 + 1];
-                            if (x0 + 2 < w) upv.z = prow[x0 + 2];
-                            if (x0 + 3 < w) upv.w = prow[x0 + 3];
-                        } else {
-                            upv = up[(step + 1) & 1][t];
-                        }
-                    }
-                    const int in[4] = {cur.x, cur.y, cur.z, cur.w};
-                    const int uv[4] = {upv.x, upv.y, upv.z, upv.w};
-                    int o[4];
-                    // The recurrence is a dependent chain through `left`, so it is kept short: with
-                    // all operands within +-2^29 (any real stream) the mean is one biased
-                    // multiply-high in 32 bits, the edge cases are selects, and the range checks
-                    // are gathered into one flag.  If the flag fails the group is redone exactly.
-                    bool ok = dc_small(left) && dc_small(upleft);
-                    {
-                        int l = left, ul = upleft;
-#pragma unroll
-                        for (int i = 0; i < 4; i++) {
-                            const int x = x0 + i;
-                            const bool interior = (x > 0) && (y > 0);
-                            const unsigned t1 = (unsigned)ul + (unsigned)uv[i] + 0xC0000001u;  // + 1 + 3*2^30
-                            const unsigned inb = (unsigned)in[i] - (1u << 30);
-                            ok = ok && dc_small(uv[i]) && dc_small(in[i]);
-                            const int q = (int)((__umulhi((unsigned)l + t1, 0xAAAAAAABu) >> 1) + inb);
-                            // first row: left; first column: up
-                            const int e = (int)((unsigned)in[i] + (unsigned)(x > 0 ? l : uv[i]));
-                            const int v = interior ? q : e;
-                            ok = ok && dc_small(v);
-                            o[i] = v;
-                            l = v;
-                            ul = uv[i];
-                        }
-                    }
-                    if (ok) {
-#pragma unroll
-                        for (int i = 0; i < 4; i++)
-                            if (x0 + i < w) maxabs = max(maxabs, o[i] < 0 ? -o[i] : o[i]);
-                        left = o[3];
-                        upleft = uv[3];
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 4; i++) {
-                            const int x = x0 + i;
-                            long long pred;
-                            if (x > 0 && y > 0) pred = floordiv3((long long)left + upleft + uv[i] + 1);
-                            else if (x > 0) pred = left;
-                            else if (y > 0) pred = uv[i];
-                            else pred = 0;
-                            o[i] = (x < w) ? narrow_or_flag((long long)in[i] + pred, &maxabs) : 0;
-                            left = o[i];
-                            upleft = uv[i];
-                        }
-                    }
-                    out = make_int4(o[0], o[1], o[2], o[3]);
-                    if (vec) {
-                        *reinterpret_cast<int4 *>(row + x0) = out;
-                    } else {
-                        row[x0] = o[0];
-                        if (x0 + 1 < w) row[x0 + 1] = o[1];
-                        if (x0 + 2 < w) row[x0 + 2] = o[2];
-                        if (x0 + 3 < w) row[x0 + 3] = o[3];
-                    }
-                }
-                up[step & 1][t + 1] = out;  // row t's values of this group, read by row t+1 next step
-                __syncthreads();
+    // inverse (encoder/pictures.py:202): the reference walks in REVERSE raster order, so every
+    // prediction is formed from neighbours that are still unmodified: out = in - pred(in).
+    // In place: tiles are visited bottom-to-top, right-to-left; a tile first stages itself
+    // plus the row above and the column to its left (both still original) in shared memory.
+    constexpr int TR = 16, TC = 64;
+    __shared__ int32_t tile[TR + 1][TC + 1];
+    for (int y0 = ((h - 1) / TR) * TR; y0 >= 0; y0 -= TR) {
+        for (int x0 = ((w - 1) / TC) * TC; x0 >= 0; x0 -= TC) {
+            for (int i = t; i < (TR + 1) * (TC + 1); i += kDcThreads) {
+                int ty = i / (TC + 1), tx = i - ty * (TC + 1);
+                int y = y0 - 1 + ty, x = x0 - 1 + tx;
+                tile[ty][tx] = (y >= 0 && y < h && x >= 0 && x < w) ? band[(size_t)y * w + x] : 0;
             }
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            __threadfence_block();
             __syncthreads();
-        }
-    } else {
-        // inverse (encoder/pictures.py:202): the reference walks in REVERSE raster order, so every
-        // prediction is formed from neighbours that are still unmodified: out = in - pred(in).
-        // In place: tiles are visited bottom-to-top, right-to-left; a tile first stages itself
-        // plus the row above and the column to its left (both still original) in shared memory.
-        constexpr int TR = 16, TC = 64;
-        __shared__ int32_t tile[TR + 1][TC + 1];
-        for (int y0 = ((h - 1) / TR) * TR; y0 >= 0; y0 -= TR) {
-            for (int x0 = ((w - 1) / TC) * TC; x0 >= 0; x0 -= TC) {
-                for (int i = t; i < (TR + 1) * (TC + 1); i += kDcThreads) {
-                    int ty = i / (TC + 1), tx = i - ty * (TC + 1);
-                    int y = y0 - 1 + ty, x = x0 - 1 + tx;
-                    tile[ty][tx] = (y >= 0 && y < h && x >= 0 && x < w) ? band[(size_t)y * w + x] : 0;
+            for (int i = t; i < TR * TC; i += kDcThreads) {
+                int ty = i / TC + 1, tx = i - (ty - 1) * TC + 1;
+                int y = y0 - 1 + ty, x = x0 - 1 + tx;
+                if (y < h && x < w) {
+                    long long pred;
+                    if (x > 0 && y > 0)
+                        pred = floordiv3((long long)tile[ty][tx - 1] + tile[ty - 1][tx - 1] + tile[ty - 1][tx] + 1);
+                    else if (x > 0) pred = tile[ty][tx - 1];
+                    else if (y > 0) pred = tile[ty - 1][tx];
+                    else pred = 0;
+                    band[(size_t)y * w + x] = narrow_or_flag((long long)tile[ty][tx] - pred, &maxabs);
                 }
-                __syncthreads();
-                for (int i = t; i < TR * TC; i += kDcThreads) {
-                    int ty = i / TC + 1, tx = i - (ty - 1) * TC + 1;
-                    int y = y0 - 1 + ty, x = x0 - 1 + tx;
-                    if (y < h && x < w) {
-                        long long pred;
-                        if (x > 0 && y > 0)
-                            pred = floordiv3((long long)tile[ty][tx - 1] + tile[ty - 1][tx - 1] + tile[ty - 1][tx] + 1);
-                        else if (x > 0) pred = tile[ty][tx - 1];
-                        else if (y > 0) pred = tile[ty - 1][tx];
-                        else pred = 0;
-                        band[(size_t)y * w + x] = narrow_or_flag((long long)tile[ty][tx] - pred, &maxabs);
-                    }
-                }
-                __syncthreads();
             }
+            __syncthreads();
         }
     }
     if (status) {
@@ -962,7 +1004,10 @@ int vc2b_dc_prediction(const vc2b_params *p, int32_t *d_coeffs, int npictures, i
     int st = make_dev_params(p, &P);
     if (st) return st;
     if (npictures <= 0) return 0;
-    dc_prediction_kernel<<<npictures * 3, kDcThreads, 0, (cudaStream_t)stream>>>(P, d_coeffs, inverse, nullptr);
+    if (inverse)
+        dc_prediction_inverse_kernel<<<npictures * 3, kDcThreads, 0, (cudaStream_t)stream>>>(P, d_coeffs, nullptr);
+    else
+        dc_prediction_fwd_kernel<<<npictures * 3, kDcWarps * 32, 0, (cudaStream_t)stream>>>(P, d_coeffs, nullptr);
     VC2B_CHECK_LAUNCH();
     return 0;
 }
@@ -1018,7 +1063,7 @@ int vc2b_unpack(const vc2b_params *p, const uint8_t *d_data, const int64_t *d_pi
     }
     if (P.is_ld) {
         // using_dc_prediction (pseudocode/parse_code_functions.py:70): LD pictures only
-        dc_prediction_kernel<<<npictures * 3, kDcThreads, 0, s>>>(P, d_coeffs, 0, d_status);
+        dc_prediction_fwd_kernel<<<npictures * 3, kDcWarps * 32, 0, s>>>(P, d_coeffs, d_status);
         VC2B_CHECK_LAUNCH();
     }
     long long safe = idwt_max_safe_coeff(p);

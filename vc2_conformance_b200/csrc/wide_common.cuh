@@ -37,6 +37,53 @@ __device__ __forceinline__ void cp_async_vec(WideVec *smem_dst, const WideVec *g
 }
 
 // One horizontal lifting stage on a row held as E[i] = column 2*NP*l + 2i, O[i] = the next one.
+// ---- L2 residency control -------------------------------------------------------------------------
+// The levels of a transform run back to back over a group of pictures small enough for the
+// intermediate LL bands to stay in the 126 MB L2 between the level that writes them and the level
+// that reads them.  That only works if the one-pass streams (coefficients in, pictures out) do not
+// push them out: streams are tagged evict_first, the intermediate bands evict_last.
+enum L2Hint : int { kL2Normal = 0, kL2EvictFirst = 1, kL2EvictLast = 2 };
+
+__device__ __forceinline__ uint64_t l2_policy(int hint)
+{
+    uint64_t pn, pf, pl;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pn));
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pf));
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pl));
+    return hint == kL2EvictFirst ? pf : (hint == kL2EvictLast ? pl : pn);
+}
+
+__device__ __forceinline__ void cp_async_vec(WideVec *smem_dst, const WideVec *gsrc, uint64_t pol)
+{
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    // keep the shared address in one plain register: with the [R + UR + imm] form ptxas (12.9) put the
+    // policy descriptor of LDGSTS in an odd uniform register and the kernel died with an illegal instruction
+    asm volatile("mov.u32 %0, %0;" : "+r"(sa));
+    if (sizeof(WideVec) == 8)
+        asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %2;" ::"r"(sa), "l"(gsrc), "l"(pol) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(sa), "l"(gsrc), "l"(pol) : "memory");
+}
+
+__device__ __forceinline__ void st_hint(void *p, const int4 &v, uint64_t pol)
+{
+    asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_hint(void *p, const uint4 &v, uint64_t pol)
+{
+    asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_hint(void *p, const int2 &v, uint64_t pol)
+{
+    asm volatile("st.global.L2::cache_hint.v2.b32 [%0], {%1, %2}, %3;" ::"l"(p), "r"(v.x), "r"(v.y), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_hint(void *p, const uint2 &v, uint64_t pol)
+{
+    asm volatile("st.global.L2::cache_hint.v2.b32 [%0], {%1, %2}, %3;" ::"l"(p), "r"(v.x), "r"(v.y), "l"(pol) : "memory");
+}
+
 template <int F, int SIDX, bool ANA, typename Ctx>
 __device__ __forceinline__ void hstage8(int (&E)[kWideNP], int (&O)[kWideNP], const Ctx &X)
 {

@@ -71,7 +71,6 @@ class BatchCodec(object):
             self.pic_offset = torch.zeros(self.max_pictures + 1, dtype=torch.int64, device=dev)
             self.data = None
             self._reserve_data(max_stream_bytes or 1 << 20)
-        self.launches = 0  # kernels enqueued by this object (bench.py reports it)
 
     # -- buffers ---------------------------------------------------------------------
     def _reserve_data(self, nbytes):
@@ -79,6 +78,11 @@ class BatchCodec(object):
         need = int(nbytes) + PAD
         if self.data is None or self.data.numel() < need:
             self.data = torch.zeros((need + 4095) // 4096 * 4096, dtype=torch.uint8, device=self.device)
+
+    @property
+    def launches(self):
+        """Kernels launched by libvc2b200 in this process so far (vc2b_launch_count)."""
+        return int(self.lib.vc2b_launch_count())
 
     def _stream_ptr(self, stream):
         torch = self.torch
@@ -132,11 +136,9 @@ class BatchCodec(object):
             capi.check("vc2b_hq_slice_offsets",
                        L.vc2b_hq_slice_offsets(C.byref(p), _ptr(d_data), _ptr(d_pic_offset), n, _ptr(so),
                                                _ptr(status), sp))
-            self.launches += 1
         capi.check("vc2b_unpack",
                    L.vc2b_unpack(C.byref(p), _ptr(d_data), _ptr(d_pic_offset), n, _ptr(so), _ptr(coeffs),
                                  _ptr(qindex), _ptr(status), sp))
-        self.launches += 4 if p.is_ld else 2
         self.idwt_device(n, stream, first)
 
     def idwt_device(self, n, stream=None, first=0):
@@ -148,7 +150,6 @@ class BatchCodec(object):
                    L.vc2b_idwt(C.byref(p), _ptr(coeffs), n, _ptr(pics), _ptr(self.scratch),
                                self.scratch.numel(), sp))
         levels = max(1, p.dwt_depth + p.dwt_depth_ho)
-        self.launches += levels * ((n + self.group - 1) // self.group)
 
     def check_status(self, n, stream=None):
         torch = self.torch
@@ -172,7 +173,6 @@ class BatchCodec(object):
                    L.vc2b_dwt(C.byref(p), _ptr(self.pictures), n, _ptr(self.coeffs), _ptr(self.scratch),
                               self.scratch.numel(), sp))
         levels = max(1, p.dwt_depth + p.dwt_depth_ho)
-        self.launches += levels * ((n + self.group - 1) // self.group)
 
     def quantize_device(self, n, picture_bytes, minimum_qindex=0, stream=None):
         """quantize_to_fit for every slice (LD: dc prediction is applied first, in place)."""
@@ -180,11 +180,9 @@ class BatchCodec(object):
         sp = self._stream_ptr(stream)
         if p.is_ld:
             capi.check("vc2b_dc_prediction", L.vc2b_dc_prediction(C.byref(p), _ptr(self.coeffs), n, 1, sp))
-            self.launches += 1
         capi.check("vc2b_quantize_to_fit",
                    L.vc2b_quantize_to_fit(C.byref(p), _ptr(self.coeffs), n, int(picture_bytes),
                                           int(minimum_qindex), _ptr(self.qindex), _ptr(self.slice_bits), sp))
-        self.launches += 1
 
     def pack_device(self, n, picture_bytes, stream=None):
         """Serialise the quantised slices; returns (device uint8 tensor [n, stride], bytes per picture)."""
@@ -199,7 +197,6 @@ class BatchCodec(object):
         capi.check("vc2b_pack_slices",
                    L.vc2b_pack_slices(C.byref(p), _ptr(self.coeffs), n, int(picture_bytes), _ptr(self.qindex),
                                       _ptr(self.slice_bits), _ptr(out), stride, sp))
-        self.launches += 2
         return out.view(n, stride), nbytes
 
     def encode_pictures(self, pictures, picture_bytes, minimum_qindex=0, stream=None):
@@ -262,7 +259,8 @@ class SequenceDecoder(object):
 
     @property
     def launches(self):
-        return sum(c.launches for c in self.codecs)
+        """Kernels launched by libvc2b200 in this process so far (vc2b_launch_count)."""
+        return int(self.codecs[0].lib.vc2b_launch_count())
 
     def plan(self, host_bytes, offsets):
         """Pre-computes per-chunk views for a packed host buffer (pinned uint8 tensor with PAD
