@@ -79,7 +79,7 @@ WORKLOADS = {
 # captures of these kernels on this workload; the summaries are committed under profiles/.
 NCU_TRAFFIC_PER_PICTURE = {
     "cfg2": {
-        "unpack": (70.9e6, "profiles/r1_v7_unpack_lanes_ncu_full_raw.csv (unpack_lanes_kernel, 32 pictures)"),
+        "unpack": (71.6e6, "profiles/r1_v9_unpack_lanes_ncu_full_raw.csv (unpack_lanes_kernel, 32 pictures: 0.215 GB read + 2.077 GB written)"),
         "idwt": (144.0e6, "profiles/r1_v4_idwt_levels_ncu.csv (4 idwt_stream8_kernel launches, 16 pictures)"),
     },
 }

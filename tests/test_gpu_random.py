@@ -244,6 +244,7 @@ def test_idwt_l2_subgroups(case, monkeypatch):
             slice_size_scaler=scaler)
     pics = [synth.noise_picture(p, 20 + i) if i % 2 == 0 else synth.ramp_picture(p, 20 + i) for i in range(7)]
     streams, decoded = _oracle_streams(p, pics, [S // 2] * len(pics))
+    monkeypatch.setenv("VC2B_IDWT_FUSED", "0")  # the fused pair of levels bypasses the per-level launches
     for group, hints in [("0", "0"), ("1", "1"), ("2", "3"), ("3", "2"), ("5", "1")]:
         monkeypatch.setenv("VC2B_IDWT_L2_GROUP", group)
         monkeypatch.setenv("VC2B_IDWT_L2_HINTS", hints)
@@ -254,3 +255,42 @@ def test_idwt_l2_subgroups(case, monkeypatch):
             planes = codec.picture_planes(i)
             for c in range(3):
                 assert (planes[c] == decoded[i][c]).all(), (case, group, hints, i, c)
+
+
+FUSED_CASES = [
+    # W, H, cw, ch, depth, wavelet, dwt_depth: several tiles across and down, ragged right / bottom edges,
+    # pictures narrower than one tile, padded dimensions
+    (1920, 1080, 960, 1080, 10, 0, 3),
+    (1000, 600, 500, 600, 10, 0, 2),
+    (1000, 600, 500, 300, 12, 1, 3),
+    (3840, 272, 1920, 272, 10, 0, 4),
+    (480, 1000, 480, 1000, 8, 1, 2),
+    (456, 130, 232, 66, 10, 0, 2),
+]
+
+
+@pytest.mark.parametrize("case", FUSED_CASES)
+def test_idwt_fused_levels(case, monkeypatch):
+    """The last two levels run in one kernel (idwt_fused2_kernel) where the filter allows it; the result
+    must equal the oracle and the one-launch-per-level path."""
+    import oracle as O
+    from vc2_conformance_b200.device import BatchCodec
+
+    W, H, cw, ch, depth, wi, d = case
+    sx, sy = 4, 2
+    S = W * H + 2 * cw * ch
+    p = _mk(luma_width=W, luma_height=H, color_diff_width=cw, color_diff_height=ch, luma_depth=depth,
+            wavelet_index=wi, dwt_depth=d, slices_x=sx, slices_y=sy,
+            slice_size_scaler=O.safe_lossy_hq_slice_size_scaler(2 * S, sx * sy))
+    pics = [synth.noise_picture(p, 40), synth.ramp_picture(p, 41), synth.noise_picture(p, 42)]
+    streams, decoded = _oracle_streams(p, pics, [S, S // 2, S // 3])
+    outs = []
+    for fused in ("1", "0"):  # opt-in fused pair, then the default per-level launches
+        monkeypatch.setenv("VC2B_IDWT_FUSED", fused)
+        codec = BatchCodec(p, len(pics))
+        codec.pictures.view(codec.torch.int16).fill_(-1)
+        codec.decode_streams(streams)
+        for i in range(len(pics)):
+            planes = codec.picture_planes(i)
+            for c in range(3):
+                assert (planes[c] == decoded[i][c]).all(), (case, fused, i, c)

@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "_lib", "libvc2b200.so")
+# VC2B_LIB: developer override (kernel variants built side by side for A/B timing)
+LIB_PATH = os.environ.get("VC2B_LIB") or os.path.join(HERE, "_lib", "libvc2b200.so")
 
 MAX_LEVELS = 16
 MAX_BANDS = 32

@@ -434,6 +434,35 @@ static int launch_level(int fv, int fh, bool vert, const LevelArgs &A, int npic,
     }
 }
 
+// The fused kernel for the last two levels (idwt8.cuh idwt_fused2_kernel): same filter in both
+// directions, four-pair vertical window, one halo lane -- Deslauriers-Dubuc (9,7) and LeGall (5,3).
+// Opt-in (VC2B_IDWT_FUSED=1; the tests run both paths): on B200 it moves 22 % less DRAM traffic per
+// picture than the two per-level launches (ncu: 112 MB against 144 MB for the last two levels of a
+// 2160p 4:2:2 picture) but takes 41 us against 24.9 us: the per-level kernels run at 88 % of the DRAM
+// peak on their traffic, while the fused CTA is latency / issue limited (12 warps per SM in lock-step
+// with a barrier per row pair, halo recomputation in 4 of 32 lanes instead of 2, and two role code
+// paths that no longer fit the instruction cache: stall_no_instruction 2.5 per issue).
+static bool fused_pair_ok(int fv, int fh)
+{
+    const char *e = getenv("VC2B_IDWT_FUSED");
+    if (!e || atoi(e) == 0) return false;
+#ifdef VC2B_DEV_BUILD
+    return fv == 0 && fh == 0;
+#else
+    return fv == fh && (fv == 0 || fv == 1);
+#endif
+}
+
+static int launch_fused_pair(int f, const LevelArgs &A3, const LevelArgs &A4, int npic, cudaStream_t s)
+{
+    static_assert(FusedCfg<0, 0>::kSupported && FusedCfg<1, 1>::kSupported, "fused pair configuration");
+    if (f == 0) return launch_fused2<0, 0>(A3, A4, npic, s);
+#ifndef VC2B_DEV_BUILD
+    if (f == 1) return launch_fused2<1, 1>(A3, A4, npic, s);
+#endif
+    return VC2B_E_UNSUPPORTED;
+}
+
 // first high-pass band index of level n (1-based)
 static int level_first_band(const DevParams &P, int n)
 {
@@ -542,7 +571,7 @@ static int run_idwt(const DevParams &P, int c0, int c1, const int32_t *coeffs, l
     A.hint_loads = (l2_hints_enabled() & 2) && npic > 1;
     // Level n over pictures [first, first + cnt): its LL input sits in scratch slots ll_slot.. (or in
     // the coefficients for n == 1), its output goes to scratch slots out_slot..
-    auto run_level = [&](int n, int first, int cnt, int ll_slot, int out_slot, bool resident_out) -> int {
+    auto fill_level = [&](int n, int first, int ll_slot, int out_slot, bool resident_out) {
         const bool vert = n > P.dwt_depth_ho;
         const bool last = n == top;
         const int fb = level_first_band(P, n);
@@ -578,8 +607,25 @@ static int run_idwt(const DevParams &P, int c0, int c1, const int32_t *coeffs, l
         A.hint_hb = A.hint_loads ? kL2EvictFirst : kL2Normal;               // read once
         A.hint_ll = (A.hint_loads && n == 1) ? kL2EvictFirst : kL2Normal;   // level-0 band: read once
         A.hint_out = !hints ? kL2Normal : (last ? kL2EvictFirst : (resident_out ? kL2EvictLast : kL2Normal));
-        return launch_level(P.wavelet_index, P.wavelet_index_ho, vert, A, cnt, s);
     };
+    auto run_level = [&](int n, int first, int cnt, int ll_slot, int out_slot, bool resident_out) -> int {
+        fill_level(n, first, ll_slot, out_slot, resident_out);
+        return launch_level(P.wavelet_index, P.wavelet_index_ho, n > P.dwt_depth_ho, A, cnt, s);
+    };
+    // last two levels in one kernel, the band between them staying on chip
+    if (pictures && P.dwt_depth >= 2 && fused_pair_ok(P.wavelet_index, P.wavelet_index_ho)) {
+        fill_level(top - 1, 0, 0, 0, false);
+        const LevelArgs A3 = A;
+        fill_level(top, 0, 0, 0, false);
+        const LevelArgs A4 = A;
+        if (level_is_wide_ok(A3, npic) && level_is_wide_ok(A4, npic)) {
+            for (int n = 1; n <= top - 2; n++) {
+                int st = run_level(n, 0, npic, 0, 0, false);
+                if (st) return st;
+            }
+            return launch_fused_pair(P.wavelet_index, A3, A4, npic, s);
+        }
+    }
     long long out_bytes = 0;  // level top-1 output per picture
     if (top >= 2)
         for (int i = 0; i < ncomp; i++) {

@@ -335,6 +335,7 @@ struct FitArgs {
     int minimum_qindex;
     int max_qm;
     int stage_cap;                // coefficients the per-warp staging area holds (quantize_fit_kernel)
+    int use_map;                  // every band fits the 24-bit offsets of FitMap
 };
 
 __device__ __forceinline__ long long hq_total_length(const DevParams &P, const FitArgs &F, long long n)
@@ -349,16 +350,101 @@ __device__ __forceinline__ long long hq_total_length(const DevParams &P, const F
 constexpr int kHintSlots = 1024;
 __device__ int g_qindex_hint[kHintSlots];
 
+// Coefficient -> (band, offset from the slice's corner of that band) map of the CTA's reference slice:
+// when every slice of the geometry has the same rectangles (all BASELINE configurations) staging a
+// coefficient is one table look-up instead of a band search and a division.
+struct FitMap {
+    uint32_t e[kStageMax];            // band << 24 | (y * band width + x); luma entries, then chroma
+    int32_t ref_w[2][kMaxBands];
+    int32_t ref_cnt[2][kMaxBands];
+    int32_t ny, nc, ok;
+};
+
+// stage one (NSRC = 1) or two (C1 and C2, same geometry) components through the map: dst[j * step] for
+// j < n.  Sixteen loads per lane are issued before the first one is used: a slice is a few hundred
+// scattered 8..64-byte row segments, and the stage is bound by their latency, not by bandwidth.
+template <int NSRC>
+__device__ __forceinline__ uint32_t stage_mapped(const uint32_t *__restrict__ map, const SliceBands &T,
+                                                 const int32_t *__restrict__ c1, const int32_t *__restrict__ c2, int n,
+                                                 int32_t *d1, uint8_t *b1, int32_t *d2, uint8_t *b2, int step, int lane)
+{
+    constexpr int U = 16 / NSRC;
+    uint32_t mx = 0;
+    for (int j0 = 0; j0 < n; j0 += 32 * U) {
+        int32_t v1[U], v2[U];
+        int bb[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int j = j0 + 32 * u + lane;
+            v1[u] = v2[u] = 0;
+            bb[u] = 0;
+            if (j < n) {
+                const uint32_t e = map[j];
+                bb[u] = (int)(e >> 24);
+                const int off = T.base[bb[u]] + (int)(e & 0xffffffu);
+                v1[u] = __ldg(c1 + off);
+                if (NSRC == 2) v2[u] = __ldg(c2 + off);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int j = j0 + 32 * u + lane;
+            if (j < n) {
+                const uint32_t m1 = v1[u] < 0 ? (uint32_t)(-(long long)v1[u]) : (uint32_t)v1[u];
+                mx = max(mx, m1);
+                d1[j * step] = (int32_t)(m1 >= 0x40000000u ? 0xffffffffu : 4u * m1);
+                b1[j * step] = (uint8_t)bb[u];
+                if (NSRC == 2) {
+                    const uint32_t m2 = v2[u] < 0 ? (uint32_t)(-(long long)v2[u]) : (uint32_t)v2[u];
+                    mx = max(mx, m2);
+                    d2[j * step] = (int32_t)(m2 >= 0x40000000u ? 0xffffffffu : 4u * m2);
+                    b2[j * step] = (uint8_t)bb[u];
+                }
+            }
+        }
+    }
+    return mx;
+}
+
 __global__ void __launch_bounds__(kQWarps * 32)
 quantize_fit_kernel(DevParams P, FitArgs F, const int32_t *__restrict__ coeffs, int npictures,
                     int32_t *__restrict__ qindex_out, int32_t *__restrict__ bits_out)
 {
     __shared__ SliceBands tabs[kQWarps][2];
+    __shared__ FitMap M;
     extern __shared__ __align__(16) unsigned char stage_mem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nslices = P.slices_x * P.slices_y;
-    const long long gw = (long long)blockIdx.x * kQWarps + warp;
-    if (gw >= (long long)npictures * nslices) return;
+    const long long total_slices = (long long)npictures * nslices;
+
+    // reference map from slice (0, 0)
+    if (warp == 0) {
+        const int ny0 = build_slice_bands(P, 0, 0, 0, tabs[0][0], lane);
+        const int nc0 = build_slice_bands(P, 1, 0, 0, tabs[0][1], lane);
+        if (lane < P.nb) {
+            for (int k = 0; k < 2; k++) {
+                M.ref_w[k][lane] = tabs[0][k].w[lane];
+                M.ref_cnt[k][lane] = tabs[0][k].cum[lane + 1] - tabs[0][k].cum[lane];
+            }
+        }
+        if (lane == 0) {
+            M.ny = ny0;
+            M.nc = nc0;
+            M.ok = F.use_map && (ny0 + nc0 <= kStageMax) && (ny0 + 2 * nc0 <= F.stage_cap);
+        }
+    }
+    __syncthreads();
+    if (M.ok) {
+        for (int j = threadIdx.x; j < M.ny + M.nc; j += kQWarps * 32) {
+            const SliceBands &T = j < M.ny ? tabs[0][0] : tabs[0][1];
+            int b;
+            const int off = locate_coeff(T, P.nb, j < M.ny ? j : j - M.ny, &b);
+            M.e[j] = ((uint32_t)b << 24) | (uint32_t)(off - T.base[b]);
+        }
+    }
+    __syncthreads();
+
+  for (long long gw = (long long)blockIdx.x * kQWarps + warp; gw < total_slices; gw += (long long)gridDim.x * kQWarps) {
     const int pic = (int)(gw / nslices);
     const int n = (int)(gw - (long long)pic * nslices);
     const int sy = n / P.slices_x, sx = n - sy * P.slices_x;
@@ -366,11 +452,33 @@ quantize_fit_kernel(DevParams P, FitArgs F, const int32_t *__restrict__ coeffs, 
     SliceBands &TY = tabs[warp][0];
     SliceBands &TC = tabs[warp][1];
     const SliceStage S = slice_stage_at(stage_mem, warp, F.stage_cap);
+    __syncwarp();
     const int ny = build_slice_bands(P, 0, sx, sy, TY, lane);
     const int nc = build_slice_bands(P, 1, sx, sy, TC, lane);
     // fast path: slice staged as 4|c| in shared memory, every magnitude below kFastMagLimit
     bool staged = (ny + 2 * nc) <= F.stage_cap;
-    if (staged) staged = stage_slice<true>(P, TY, TC, pc, ny, nc, S, lane) < kFastMagLimit;
+    if (staged) {
+        bool same = M.ok != 0;
+        if (same && lane < P.nb)
+            same = TY.w[lane] == M.ref_w[0][lane] && TY.cum[lane + 1] - TY.cum[lane] == M.ref_cnt[0][lane] &&
+                   TC.w[lane] == M.ref_w[1][lane] && TC.cum[lane + 1] - TC.cum[lane] == M.ref_cnt[1][lane];
+        uint32_t mx;
+        if (__all_sync(0xffffffffu, same)) {
+            const int32_t *c0 = pc + P.comp_off[0], *c1 = pc + P.comp_off[1], *c2 = pc + P.comp_off[2];
+            mx = stage_mapped<1>(M.e, TY, c0, nullptr, ny, S.coef, S.band, nullptr, nullptr, 1, lane);
+            if (P.is_ld)
+                mx = max(mx, stage_mapped<2>(M.e + ny, TC, c1, c2, nc, S.coef + ny, S.band + ny, S.coef + ny + 1,
+                                             S.band + ny + 1, 2, lane));
+            else
+                mx = max(mx, stage_mapped<2>(M.e + ny, TC, c1, c2, nc, S.coef + ny, S.band + ny, S.coef + ny + nc,
+                                             S.band + ny + nc, 1, lane));
+            __syncwarp();
+            mx = __reduce_max_sync(0xffffffffu, mx);
+        } else {
+            mx = stage_slice<true>(P, TY, TC, pc, ny, nc, S, lane);
+        }
+        staged = mx < kFastMagLimit;
+    }
 
     long long target, align;
     if (P.is_ld) {
@@ -458,6 +566,7 @@ quantize_fit_kernel(DevParams P, FitArgs F, const int32_t *__restrict__ coeffs, 
             bits_out[3 * gw + 2] = bc2;
         }
     }
+  }  // slices of this warp
 }
 
 // ---------------------------------------------------------------------------
@@ -695,9 +804,21 @@ int vc2b_quantize_to_fit(const vc2b_params *p, const int32_t *d_coeffs, int npic
             cap += (long long)((P.band[c][b].w + P.slices_x - 1) / P.slices_x) *
                    ((P.band[c][b].h + P.slices_y - 1) / P.slices_y);
     F.stage_cap = cap <= kStageMax ? (int)((cap + 15) & ~15LL) : 16;  // larger slices are searched unstaged
+    F.use_map = 1;
+    for (int c = 0; c < 3; c++)
+        for (int b = 0; b < P.nb; b++)
+            if ((long long)P.band[c][b].w * P.band[c][b].h >= (1 << 24)) F.use_map = 0;
     const size_t smem = kQWarps * slice_stage_bytes(F.stage_cap);
+    {   // static + dynamic shared memory can exceed the 48 KB default for the largest staged slices
+        static const cudaError_t attr = cudaFuncSetAttribute(quantize_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                             (int)(kQWarps * slice_stage_bytes(kStageMax)));
+        if (attr != cudaSuccess) return (int)attr;
+    }
     const long long warps = npictures * nslices;
-    quantize_fit_kernel<<<(unsigned)((warps + kQWarps - 1) / kQWarps), kQWarps * 32, smem, (cudaStream_t)stream>>>(
+    // persistent CTAs: each warp walks slices gw, gw + grid * kQWarps, ... (the reference map is built once per CTA)
+    long long nblk = (warps + kQWarps - 1) / kQWarps;
+    if (nblk > 148LL * 16) nblk = 148LL * 16;
+    quantize_fit_kernel<<<(unsigned)nblk, kQWarps * 32, smem, (cudaStream_t)stream>>>(
         P, F, d_coeffs, npictures, d_qindex, d_slice_bits);
     VC2B_CHECK_LAUNCH();
     return 0;
@@ -738,6 +859,7 @@ int vc2b_pack_slices(const vc2b_params *p, const int32_t *d_coeffs, int npicture
     F.minimum_qindex = 0;
     F.max_qm = max_qm(P);
     F.stage_cap = 0;
+    F.use_map = 0;
     cudaStream_t s = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(d_out, 0, (size_t)out_stride * npictures, s);
     if (e != cudaSuccess) return (int)e;

@@ -736,7 +736,8 @@ __device__ __forceinline__ long long floordiv3(long long v)
     return (v - q * 3 < 0) ? q - 1 : q;
 }
 
-__device__ __forceinline__ bool dc_small(int v) { return (unsigned)v + (1u << 29) < (1u << 30); }
+// |v| < 2^28: three such values plus the bias 3*2^30 + 1 stay below 2^32 (fast path of dc_group)
+__device__ __forceinline__ bool dc_small(int v) { return (unsigned)v + (1u << 28) < (1u << 29); }
 
 // Narrows to int32 and keeps the running max |value| in *maxabs (0x7fffffff: left the envelope).
 __device__ __forceinline__ int narrow_or_flag(long long v, int *maxabs)
@@ -763,42 +764,52 @@ constexpr int kDcWarps = 8;      // rows per pass = 32 * kDcWarps
 constexpr int kDcAhead = 8;      // groups prefetched ahead (register ring; loop unrolled by it)
 
 struct DcLane {
-    int left, upleft, maxabs;
+    int left, upleft;
+    int maxabs;       // from the exact path (0x7fffffff: left the int32 envelope)
+    int vmin, vmax;   // range of the values produced by the fast path
 };
 
-// four columns of one row: `in` the residues, `uv` the finished row above; returns the finished values
+// four columns of one row: `cur` the residues, `upv` the finished row above; returns the finished values.
+// first_group: x0 == 0.  EDGE: w is not a multiple of four (columns >= w are padding).
+template <bool EDGE>
 __device__ __forceinline__ int4 dc_group(DcLane &L, const int4 cur, const int4 upv, int x0, int y, int w)
 {
     const int in[4] = {cur.x, cur.y, cur.z, cur.w};
     const int uv[4] = {upv.x, upv.y, upv.z, upv.w};
     int o[4];
     // The recurrence is a dependent chain through `left`, so it is kept short: with all operands within
-    // +-2^29 (any real stream) the mean is one biased multiply-high in 32 bits, the edge cases are
-    // selects, and the range checks are gathered into one flag.  If the flag fails the group is redone
-    // exactly in 64 bits.
-    bool ok = dc_small(L.left) && dc_small(L.upleft);
+    // +-2^28 (any real stream) the mean is one biased multiply-high in 32 bits, the edge cases are
+    // selects off the chain, and the range checks are OR-ed into one word tested once per group.  If
+    // the test fails the group is redone exactly in 64 bits.
+    constexpr unsigned B = 1u << 28;
+    const bool ypos = y > 0, xpos = x0 > 0;
+    unsigned rng = ((unsigned)L.left + B) | ((unsigned)L.upleft + B);
     {
         int l = L.left, ul = L.upleft;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            const int x = x0 + i;
-            const bool interior = (x > 0) && (y > 0);
             const unsigned t1 = (unsigned)ul + (unsigned)uv[i] + 0xC0000001u;  // + 1 + 3*2^30
             const unsigned inb = (unsigned)in[i] - (1u << 30);
-            ok = ok && dc_small(uv[i]) && dc_small(in[i]);
+            rng |= ((unsigned)uv[i] + B) | ((unsigned)in[i] + B);
             const int q = (int)((__umulhi((unsigned)l + t1, 0xAAAAAAABu) >> 1) + inb);
-            const int e = (int)((unsigned)in[i] + (unsigned)(x > 0 ? l : uv[i]));  // first row: left; first column: up
-            const int v = interior ? q : e;
-            ok = ok && dc_small(v);
+            // first row: left; first column: up (zero in the corner)
+            const bool has_left = (i > 0) || xpos;
+            const int e = (int)((unsigned)in[i] + (unsigned)(has_left ? l : uv[i]));
+            const int v = (has_left && ypos) ? q : e;
+            rng |= (unsigned)v + B;
             o[i] = v;
             l = v;
             ul = uv[i];
         }
     }
-    if (ok) {
+    if ((rng >> 29) == 0) {
 #pragma unroll
-        for (int i = 0; i < 4; i++)
-            if (x0 + i < w) L.maxabs = max(L.maxabs, o[i] < 0 ? -o[i] : o[i]);
+        for (int i = 0; i < 4; i++) {
+            if (!EDGE || x0 + i < w) {
+                L.vmin = min(L.vmin, o[i]);
+                L.vmax = max(L.vmax, o[i]);
+            }
+        }
         L.left = o[3];
         L.upleft = uv[3];
     } else {
@@ -822,6 +833,7 @@ __global__ void __launch_bounds__(kDcWarps * 32)
 dc_prediction_fwd_kernel(DevParams P, int32_t *__restrict__ coeffs, int32_t *__restrict__ status)
 {
     __shared__ volatile int progress[kDcWarps];  // groups of the warp's last row that are final in global memory
+    const int nwarps = blockDim.x >> 5;
     const int pic = blockIdx.x / 3, comp = blockIdx.x % 3;
     const Band &B = P.band[comp][0];
     const int w = B.w, h = B.h;
@@ -831,29 +843,39 @@ dc_prediction_fwd_kernel(DevParams P, int32_t *__restrict__ coeffs, int32_t *__r
     const bool vec = (w & 3) == 0 && ((reinterpret_cast<uintptr_t>(band) & 15) == 0);
     DcLane L;
     L.maxabs = 0;
+    L.vmin = 0;
+    L.vmax = 0;
 
     // Rows are read 16 bytes at a time with a row stride between neighbouring lanes, which is a poor
     // DRAM pattern: pull the band into L2 first with one coalesced sweep of prefetches.
     {
         const char *b0 = reinterpret_cast<const char *>(band);
         const size_t nbytes = (size_t)w * h * sizeof(int32_t);
-        for (size_t off = (size_t)threadIdx.x * 128; off < nbytes; off += (size_t)kDcWarps * 32 * 128)
+        for (size_t off = (size_t)threadIdx.x * 128; off < nbytes; off += (size_t)blockDim.x * 128)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(b0 + off));
     }
 
-    auto load_group = [&](const int32_t *row, int g) -> int4 {  // group g of a row (L2; never L1: rows above are
-        int4 v = make_int4(0, 0, 0, 0);                          // written by another warp)
-        if (g < 0 || g >= ngroups) return v;
-        if (vec) return __ldcg(reinterpret_cast<const int4 *>(row) + g);
-        const int x = 4 * g;
-        v.x = __ldcg(row + x);
-        if (x + 1 < w) v.y = __ldcg(row + x + 1);
-        if (x + 2 < w) v.z = __ldcg(row + x + 2);
-        if (x + 3 < w) v.w = __ldcg(row + x + 3);
-        return v;
+    // Own rows (and, for the first warp of a later pass, the final row above) are staged eight steps
+    // ahead by cp.async into lane-private shared-memory slots, one commit group per step.
+    __shared__ int4 stage[kDcAhead][kDcWarps * 32];
+    __shared__ int4 stage_up[kDcAhead][kDcWarps];
+    auto async_group = [&](int4 *dst, const int32_t *row, int g) {
+        if (g < 0 || g >= ngroups) return;
+        if (vec) {
+            const unsigned sa = (unsigned)__cvta_generic_to_shared(dst);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(row + 4 * g) : "memory");
+        } else {
+            int4 v = make_int4(0, 0, 0, 0);
+            const int x = 4 * g;
+            v.x = __ldcg(row + x);
+            if (x + 1 < w) v.y = __ldcg(row + x + 1);
+            if (x + 2 < w) v.z = __ldcg(row + x + 2);
+            if (x + 3 < w) v.w = __ldcg(row + x + 3);
+            *dst = v;
+        }
     };
 
-    for (int y0 = 0; y0 < h; y0 += 32 * kDcWarps) {
+    for (int y0 = 0; y0 < h; y0 += 32 * nwarps) {
         if (threadIdx.x < kDcWarps) progress[threadIdx.x] = 0;
         __syncthreads();
         const int yw = y0 + 32 * wb;          // first row of this warp
@@ -868,17 +890,17 @@ dc_prediction_fwd_kernel(DevParams P, int32_t *__restrict__ coeffs, int32_t *__r
             auto wait_for = [&](int g) {
                 if (!wait_above) return;
                 const int need = min(g, ngroups - 1) + 1;
-                while (progress[wb - 1] < need) { }
+                while (progress[wb - 1] < need) __nanosleep(64);
                 __threadfence_block();
             };
             L.left = 0;
             L.upleft = 0;
-            int4 ring[kDcAhead], upring[kDcAhead];
             wait_for(kDcAhead - 1);
 #pragma unroll
             for (int u = 0; u < kDcAhead; u++) {
-                ring[u] = row_ok ? load_group(row, u - lane) : make_int4(0, 0, 0, 0);
-                upring[u] = (lane == 0 && has_above) ? load_group(above, u) : make_int4(0, 0, 0, 0);
+                if (row_ok) async_group(&stage[u][threadIdx.x], row, u - lane);
+                if (lane == 0 && has_above) async_group(&stage_up[u][wb], above, u);
+                asm volatile("cp.async.commit_group;" ::: "memory");
             }
             int4 prev = make_int4(0, 0, 0, 0);   // this lane's output of the previous step
             const int nsteps = ngroups + 31;
@@ -888,24 +910,27 @@ dc_prediction_fwd_kernel(DevParams P, int32_t *__restrict__ coeffs, int32_t *__r
                 for (int u = 0; u < kDcAhead; u++) {
                     const int s = s0 + u;
                     const int g = s - lane;
+                    asm volatile("cp.async.wait_group %0;" ::"n"(kDcAhead - 1) : "memory");
                     int4 upv;
                     upv.x = __shfl_up_sync(0xffffffffu, prev.x, 1);
                     upv.y = __shfl_up_sync(0xffffffffu, prev.y, 1);
                     upv.z = __shfl_up_sync(0xffffffffu, prev.z, 1);
                     upv.w = __shfl_up_sync(0xffffffffu, prev.w, 1);
-                    if (lane == 0) upv = upring[u];
-                    const int4 cur = ring[u];
+                    if (lane == 0) upv = has_above ? stage_up[u][wb] : make_int4(0, 0, 0, 0);
+                    const int4 cur = stage[u][threadIdx.x];
                     // refill the slots with the groups of step s + kDcAhead
-                    ring[u] = row_ok ? load_group(row, g + kDcAhead) : make_int4(0, 0, 0, 0);
-                    if (lane == 0 && has_above) upring[u] = load_group(above, s + kDcAhead);
+                    if (row_ok) async_group(&stage[u][threadIdx.x], row, g + kDcAhead);
+                    if (lane == 0 && has_above) async_group(&stage_up[u][wb], above, s + kDcAhead);
+                    asm volatile("cp.async.commit_group;" ::: "memory");
                     int4 out = make_int4(0, 0, 0, 0);
                     const bool active = row_ok && g >= 0 && g < ngroups;
                     if (active) {
                         const int x0 = 4 * g;
-                        out = dc_group(L, cur, upv, x0, y, w);
                         if (vec) {
+                            out = dc_group<false>(L, cur, upv, x0, y, w);
                             *reinterpret_cast<int4 *>(row + x0) = out;
                         } else {
+                            out = dc_group<true>(L, cur, upv, x0, y, w);
                             row[x0] = out.x;
                             if (x0 + 1 < w) row[x0 + 1] = out.y;
                             if (x0 + 2 < w) row[x0 + 2] = out.z;
@@ -919,14 +944,14 @@ dc_prediction_fwd_kernel(DevParams P, int32_t *__restrict__ coeffs, int32_t *__r
                     prev = out;
                 }
             }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __threadfence_block();
         __syncthreads();   // rows of this pass are final for the next one
     }
     if (status) {
-        int maxabs = L.maxabs;
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) maxabs = max(maxabs, __shfl_xor_sync(0xffffffffu, maxabs, d));
+        int maxabs = max(L.maxabs, max(-L.vmin, L.vmax));  // fast-path values are within +-2^28
+        maxabs = __reduce_max_sync(0xffffffffu, maxabs);
         if (lane == 0 && maxabs) atomicMax(&status[4 * pic + 3], maxabs);
     }
 }
@@ -978,6 +1003,13 @@ dc_prediction_inverse_kernel(DevParams P, int32_t *__restrict__ coeffs, int32_t 
     }
 }
 
+static int launch_dc_fwd(const DevParams &P, int32_t *d_coeffs, int npictures, int32_t *d_status, cudaStream_t s)
+{
+    dc_prediction_fwd_kernel<<<npictures * 3, kDcWarps * 32, 0, s>>>(P, d_coeffs, d_status);
+    VC2B_CHECK_LAUNCH();
+    return 0;
+}
+
 }  // namespace vc2b
 
 using namespace vc2b;
@@ -1007,7 +1039,7 @@ int vc2b_dc_prediction(const vc2b_params *p, int32_t *d_coeffs, int npictures, i
     if (inverse)
         dc_prediction_inverse_kernel<<<npictures * 3, kDcThreads, 0, (cudaStream_t)stream>>>(P, d_coeffs, nullptr);
     else
-        dc_prediction_fwd_kernel<<<npictures * 3, kDcWarps * 32, 0, (cudaStream_t)stream>>>(P, d_coeffs, nullptr);
+        return launch_dc_fwd(P, d_coeffs, npictures, nullptr, (cudaStream_t)stream);
     VC2B_CHECK_LAUNCH();
     return 0;
 }
@@ -1063,8 +1095,8 @@ int vc2b_unpack(const vc2b_params *p, const uint8_t *d_data, const int64_t *d_pi
     }
     if (P.is_ld) {
         // using_dc_prediction (pseudocode/parse_code_functions.py:70): LD pictures only
-        dc_prediction_fwd_kernel<<<npictures * 3, kDcWarps * 32, 0, s>>>(P, d_coeffs, d_status);
-        VC2B_CHECK_LAUNCH();
+        st = launch_dc_fwd(P, d_coeffs, npictures, d_status, s);
+        if (st) return st;
     }
     long long safe = idwt_max_safe_coeff(p);
     if (safe > 0x7ffffffeLL) safe = 0x7ffffffeLL;  // 0x7fffffff marks a value that did not fit int32
