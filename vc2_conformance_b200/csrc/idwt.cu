@@ -341,6 +341,7 @@ idwt_stream_kernel(LevelArgs A)
 }  // namespace vc2b
 
 #include "idwt8.cuh"
+#include "idwt_ring.cuh"
 
 namespace vc2b {
 
@@ -371,7 +372,10 @@ static int launch_level_t(const LevelArgs &A_in, int npic, cudaStream_t s)
 {
     LevelArgs A = A_in;
     int maxtiles = 0;
-    if constexpr (VERT && Strip8Cfg<FV, FH>::kSupported && (FV == FH || (FV == 5 && FH == 6))) {
+    if constexpr (VERT && FV == 5 && RingCfg<FV, FH>::kSupported) {  // Fidelity: vertical window in shared memory
+        if (level_is_wide_ok(A, npic)) return launch_ring<FV, FH>(A, npic, s);
+    }
+    if constexpr (VERT && FV != 5 && Strip8Cfg<FV, FH>::kSupported && FV == FH) {
         if (level_is_wide_ok(A, npic)) return launch_wide<FV, FH>(A, npic, s);
     }
     if constexpr (VERT) {

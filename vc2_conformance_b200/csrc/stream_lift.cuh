@@ -90,13 +90,20 @@ struct PairRing {
     int v[2][NC][RING];
 };
 
-// Weighted sum of L taps; every VC-2 filter has symmetric taps, so equal outer pairs are folded
-// (tap * (a + b)) to halve the multiplies.  get(i) returns the i-th source sample.
+// Weighted sum of L taps plus `init` (the rounding constant).  32-bit sums: every VC-2 filter has
+// symmetric taps, so equal outer pairs are folded (tap * (a + b)) to halve the multiplies.  64-bit sums
+// (Fidelity, Daubechies): NOT folded -- a + b needs a 64-bit add before a 64 x 64 multiply, while
+// tap * a accumulates in a single IMAD.WIDE.  get(i) returns the i-th source sample.
 template <int SIDX_L, typename Acc, typename Get>
-__device__ __forceinline__ Acc folded_taps(const int (&taps)[8], Get get)
+__device__ __forceinline__ Acc folded_taps(const int (&taps)[8], Get get, Acc init = 0)
 {
     constexpr int L = SIDX_L;
-    Acc sum = 0;
+    Acc sum = init;
+    if (sizeof(Acc) == 8) {
+#pragma unroll
+        for (int i = 0; i < L; i++) sum += (Acc)taps[i] * (Acc)get(i);
+        return sum;
+    }
 #pragma unroll
     for (int i = 0; i < L / 2; i++) {
         if (taps[i] == taps[L - 1 - i]) {
@@ -141,8 +148,7 @@ __device__ __forceinline__ void vstage_fast(PairRing<RING, NC> &R)
     for (int c = 0; c < NC; c++) {
         Acc sum = folded_taps<st.L, Acc>(st.taps, [&](int i) {
             return R.v[1 - par][c][(k + P.dmin[SIDX] + i) & (RING - 1)];
-        });
-        if (st.S > 0) sum += (Acc)1 << (st.S > 0 ? st.S - 1 : 0);
+        }, st.S > 0 ? (Acc)1 << (st.S > 0 ? st.S - 1 : 0) : (Acc)0);
         sum >>= st.S;
         if (add) R.v[par][c][k & (RING - 1)] += (int)sum;
         else R.v[par][c][k & (RING - 1)] -= (int)sum;

@@ -117,8 +117,8 @@ __device__ __forceinline__ void hstage8(int (&E)[kWideNP], int (&O)[kWideNP], co
     }
 #pragma unroll
     for (int i = 0; i < NP; i++) {
-        Acc sum = folded_taps<st.L, Acc>(st.taps, [&](int t) { return ext[NP + i + dmin + t]; });
-        if (st.S > 0) sum += (Acc)1 << (st.S > 0 ? st.S - 1 : 0);
+        Acc sum = folded_taps<st.L, Acc>(st.taps, [&](int t) { return ext[NP + i + dmin + t]; },
+                                         st.S > 0 ? (Acc)1 << (st.S > 0 ? st.S - 1 : 0) : (Acc)0);
         sum >>= st.S;
         if (even) { if (add) E[i] += (int)sum; else E[i] -= (int)sum; }
         else { if (add) O[i] += (int)sum; else O[i] -= (int)sum; }
