@@ -179,6 +179,22 @@ int vc2b_forward_quant(const int32_t *d_in, const int32_t *d_qi, int32_t *d_out,
  * mode bit0 = clip, bit1 = add offset, bit2 = subtract offset (remove_offset, :264). */
 int vc2b_clip_offset(int32_t *d_data, int64_t n, int depth, int mode, void *stream);
 
+/* ---- raw picture files and picture comparison --------------------- */
+/* Bytes of one picture in the reference's raw planar file format: components Y, C1, C2, little
+ * endian, ceil(depth / 8) rounded up to a power of two bytes per sample
+ * (file_format.py:158-194, dimensions_and_depths.py:46-86). */
+int64_t vc2b_raw_picture_bytes(const vc2b_params *p);
+/* file_format.write_picture for npictures device pictures: d_raw[i * raw_stride ...] gets picture i. */
+int vc2b_pictures_to_raw(const vc2b_params *p, const uint16_t *d_pictures, int npictures, uint8_t *d_raw,
+                         int64_t raw_stride, void *stream);
+/* file_format.read_picture (:263-314), including the masking of the bits above the sample depth. */
+int vc2b_raw_to_pictures(const vc2b_params *p, const uint8_t *d_raw, int64_t raw_stride, int npictures,
+                         uint16_t *d_pictures, void *stream);
+/* scripts/vc2_picture_compare.py:370-420 measure_differences: d_result[(i * 3 + c) * 2 + {0, 1}] =
+ * {samples of component c of picture i that differ, sum of their squared differences}. */
+int vc2b_picture_compare(const vc2b_params *p, const uint16_t *d_a, const uint16_t *d_b, int npictures,
+                         uint64_t *d_result, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -93,6 +93,10 @@ SIGNATURES = {
     "vc2b_inverse_quant": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "vc2b_forward_quant": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "vc2b_clip_offset": (_i, [_vp, _i64, _i, _i, _vp]),
+    "vc2b_raw_picture_bytes": (_i64, [_PP]),
+    "vc2b_pictures_to_raw": (_i, [_PP, _vp, _i, _vp, _i64, _vp]),
+    "vc2b_raw_to_pictures": (_i, [_PP, _vp, _i64, _i, _vp, _vp]),
+    "vc2b_picture_compare": (_i, [_PP, _vp, _vp, _i, _vp, _vp]),
 }
 
 
