@@ -1,6 +1,7 @@
 """
 Minimal stand-in for the ``bitarray`` package (absent from this image), just
-enough for /root/reference/vc2_conformance/bitstream/{io,vc2_fixeddicts}.py.
+enough for /root/reference/vc2_conformance/bitstream/{io,vc2_fixeddicts}.py and
+test_cases/decoder/pictures.py.
 TEST INFRASTRUCTURE ONLY (golden-vector generation; see oracle/ref_import.py).
 """
 
@@ -43,6 +44,13 @@ class bitarray(object):
 
     def __hash__(self):
         return hash(tuple(self._bits))
+
+    def frombytes(self, data):
+        """bitarray.frombytes: appends the bits of `data`, most significant bit of each byte first
+        (the real package's default big-endian bit order, which the reference relies on)."""
+        for byte in bytearray(data):
+            for k in range(7, -1, -1):
+                self._bits.append((byte >> k) & 1)
 
     def to01(self):
         return "".join(str(b) for b in self._bits)
