@@ -111,22 +111,6 @@ __device__ __forceinline__ void load_pair8(const Strip8Ctx &X, const WideVec *sm
     vec_to_array(so[96], r.b2);
 }
 
-// Pull rows that will be needed kWidePrefetchL2 steps from now into L2 (two row pairs per call):
-// a strip reads four row streams with a large stride, which no hardware prefetcher follows.
-constexpr int kWidePrefetchL2 = 16;
-__device__ __forceinline__ void prefetch_pairs_l2(const Strip8Ctx &X, int m)
-{
-    if (m + 1 < X.h) {
-        const int idx = m * X.wq + X.jqc + ((X.lane & 1) ? X.wq : 0);  // even lanes row m, odd lanes row m+1
-        if ((X.lane & 14) == 0) {  // lanes 0,1,16,17: one request per 128-byte line and row
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(X.ll + idx));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(X.b0 + idx));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(X.b1 + idx));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(X.b2 + idx));
-        }
-    }
-}
-
 // LL/HL feed the even row (even/odd columns), LH/HH the odd row (vh_synthesis :164-169)
 template <int RING>
 __device__ __forceinline__ void put_pair8(PairRing<RING, kWideNC> &R, int slot_even, int slot_odd, const RawPair &r)
