@@ -195,6 +195,37 @@ int vc2b_raw_to_pictures(const vc2b_params *p, const uint8_t *d_raw, int64_t raw
 int vc2b_picture_compare(const vc2b_params *p, const uint16_t *d_a, const uint16_t *d_b, int npictures,
                          uint64_t *d_result, void *stream);
 
+/* ---- stream index (host code, no device work) ------------------------ */
+/* vc2b_unit.flags */
+#define VC2B_IDX_NEEDS_BASE_FORMAT 1           /* dimensions / depths come from the base video format table */
+#define VC2B_IDX_NEEDS_DEFAULT_QUANT_MATRIX 2  /* custom_quant_matrix is false: default matrix table */
+#define VC2B_IDX_NO_SEQUENCE_HEADER 4          /* picture before any sequence header */
+#define VC2B_IDX_TRUNCATED 8                   /* the stream ended inside this data unit's header */
+#define VC2B_IDX_UNSUPPORTED 16                /* more transform levels than VC2B_MAX_LEVELS */
+
+/* One data unit of a VC-2 stream (parse_info, decoder/stream.py:194): where it starts, and for
+ * pictures (parse codes 0xC8 / 0xE8) and fragments (0xCC / 0xEC) the picture-path parameters
+ * (picture_syntax.py:94-348, fragment_syntax.py:55-140, video_parameters.py:177-206) and the byte
+ * offset of the transform data (pictures) or of the fragment's slices that vc2b_hq_slice_offsets /
+ * vc2b_unpack take. */
+typedef struct vc2b_unit {
+    int64_t offset;        /* of the parse_info prefix 0x42424344 */
+    int64_t next_offset;   /* offset + next_parse_offset, 0 if the stream gives none */
+    int64_t data_offset;   /* transform data / slice data, -1 if the unit has none */
+    int32_t parse_code;
+    int32_t flags;         /* VC2B_IDX_* */
+    uint32_t picture_number;
+    int32_t fragment_data_length, fragment_slice_count, fragment_x_offset, fragment_y_offset;
+    int32_t major_version, minor_version, profile, level, base_video_format, picture_coding_mode;
+    vc2b_params params;    /* pictures and fragments; zero where a flag says the stream does not define it */
+} vc2b_unit;
+
+/* Walks the data units of `data` (HOST memory) from offset 0 (parse_sequence, decoder/stream.py:96-138)
+ * following next_parse_offset (for pictures without one: the slice lengths).  Writes up to max_units
+ * entries and returns the number of data units found (which may exceed max_units), or VC2B_E_BAD_PARAMS
+ * if the buffer does not start with a parse_info header.  Performs no conformance checks. */
+int64_t vc2b_index_stream(const uint8_t *data, int64_t len, vc2b_unit *units, int64_t max_units);
+
 #ifdef __cplusplus
 }
 #endif

@@ -48,6 +48,37 @@ class Params(C.Structure):
     ]
 
 
+class Unit(C.Structure):
+    """struct vc2b_unit (include/vc2_b200.h): one data unit found by vc2b_index_stream."""
+
+    _fields_ = [
+        ("offset", C.c_int64),
+        ("next_offset", C.c_int64),
+        ("data_offset", C.c_int64),
+        ("parse_code", C.c_int32),
+        ("flags", C.c_int32),
+        ("picture_number", C.c_uint32),
+        ("fragment_data_length", C.c_int32),
+        ("fragment_slice_count", C.c_int32),
+        ("fragment_x_offset", C.c_int32),
+        ("fragment_y_offset", C.c_int32),
+        ("major_version", C.c_int32),
+        ("minor_version", C.c_int32),
+        ("profile", C.c_int32),
+        ("level", C.c_int32),
+        ("base_video_format", C.c_int32),
+        ("picture_coding_mode", C.c_int32),
+        ("params", Params),
+    ]
+
+
+IDX_NEEDS_BASE_FORMAT = 1
+IDX_NEEDS_DEFAULT_QUANT_MATRIX = 2
+IDX_NO_SEQUENCE_HEADER = 4
+IDX_TRUNCATED = 8
+IDX_UNSUPPORTED = 16
+
+
 class LibraryMissing(ImportError):
     pass
 
@@ -97,6 +128,7 @@ SIGNATURES = {
     "vc2b_pictures_to_raw": (_i, [_PP, _vp, _i, _vp, _i64, _vp]),
     "vc2b_raw_to_pictures": (_i, [_PP, _vp, _i64, _i, _vp, _vp]),
     "vc2b_picture_compare": (_i, [_PP, _vp, _vp, _i, _vp, _vp]),
+    "vc2b_index_stream": (_i64, [_vp, _i64, _vp, _i64]),
 }
 
 
