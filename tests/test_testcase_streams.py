@@ -19,10 +19,15 @@ def _base(name):
     return name.split(".", 1)[0]
 
 
+def _params_key(z, name):
+    """lossless_quantization streams carry their own slice_size_scaler; the others share their picture's."""
+    return name + ".params" if name + ".params" in z.files else _base(name) + ".params"
+
+
 @pytest.mark.parametrize("name", _names())
 def test_oracle_decodes_testcase_stream(name):
     z = load("testcases")
-    p = params_from_arrays(z[_base(name) + ".params"], z[_base(name) + ".quant_matrix"])
+    p = params_from_arrays(z[_params_key(z, name)], z[_base(name) + ".quant_matrix"])
     data = z[name + ".data"].tobytes()
     st, out, consumed = O.decode_picture(p, data)
     assert st == 0 and consumed == len(data)
@@ -33,7 +38,8 @@ def test_oracle_decodes_testcase_stream(name):
 def test_all_kinds_present():
     names = _names()
     for kind in ("all_zeros", "all_ones", "alternating_1s_and_0s", "alternating_0s_and_1s", "dummy_end_of_sequence",
-                 "zero_dangling", "sign_dangling", "stop_and_sign_dangling", "lsb_stop_and_sign_dangling"):
+                 "zero_dangling", "sign_dangling", "stop_and_sign_dangling", "lsb_stop_and_sign_dangling",
+                 "lossless_quantization"):
         assert any(kind in n for n in names), kind
     assert any(n.startswith("hq_") for n in names) and any(n.startswith("ld_") for n in names)
 
@@ -45,17 +51,21 @@ def test_device_decodes_testcase_streams(base, unpack_kernel):
     from vc2_conformance_b200.params import params_from_arrays as dev_params
 
     z = load("testcases")
-    p = dev_params(z[base + ".params"], z[base + ".quant_matrix"])
-    names = [n for n in _names() if _base(n) == base]
-    streams = [z[n + ".data"].tobytes() for n in names]
-    codec = BatchCodec(p, len(names))
-    codec.decode_streams(streams)
-    st = codec.status_host(len(names))
-    assert (st[:, 0] == 0).all()
-    assert (st[:, 2] == np.array([len(s) for s in streams])).all()
-    for i, n in enumerate(names):
-        coeffs = codec.coeff_components(i)
-        planes = codec.picture_planes(i)
-        for c in range(3):
-            assert (coeffs[c] == z[n + ".dec_coeffs%d" % c]).all(), (n, "coeffs", c)
-            assert (planes[c] == z[n + ".decoded%d" % c]).all(), (n, "picture", c)
+    groups = {}
+    for n in _names():
+        if _base(n) == base:
+            groups.setdefault(_params_key(z, n), []).append(n)
+    for key, names in groups.items():
+        p = dev_params(z[key], z[base + ".quant_matrix"])
+        streams = [z[n + ".data"].tobytes() for n in names]
+        codec = BatchCodec(p, len(names))
+        codec.decode_streams(streams)
+        st = codec.status_host(len(names))
+        assert (st[:, 0] == 0).all()
+        assert (st[:, 2] == np.array([len(s) for s in streams])).all()
+        for i, n in enumerate(names):
+            coeffs = codec.coeff_components(i)
+            planes = codec.picture_planes(i)
+            for c in range(3):
+                assert (coeffs[c] == z[n + ".dec_coeffs%d" % c]).all(), (n, "coeffs", c)
+                assert (planes[c] == z[n + ".decoded%d" % c]).all(), (n, "picture", c)

@@ -1,5 +1,6 @@
-"""Parity streams restating the reference's decoder test-case generators `slice_padding_data` and
-`dangling_bounded_block_data` (test_cases/decoder/pictures.py:645-880).
+"""Parity streams restating the reference's decoder test-case generators `slice_padding_data`,
+`dangling_bounded_block_data` (test_cases/decoder/pictures.py:645-880) and `lossless_quantization`
+(test_cases/decoder/lossless_quantization.py:117).
 
 The generators themselves need whole sequences and the codec-feature tables; what makes their streams
 special is done by four helpers that act on one slice -- fill_hq_slice_padding (:89),
@@ -43,6 +44,7 @@ _dpkg = types.ModuleType("vc2_conformance.test_cases.decoder")
 _dpkg.__path__ = [os.path.join(_tc_dir, "decoder")]
 sys.modules["vc2_conformance.test_cases.decoder"] = _dpkg
 tcp = importlib.import_module("vc2_conformance.test_cases.decoder.pictures")
+tcl = importlib.import_module("vc2_conformance.test_cases.decoder.lossless_quantization")
 from vc2_data_tables import Profiles  # noqa: E402
 
 O = MG.O
@@ -103,11 +105,39 @@ def main():
             for comp in comps:
                 variants.append(("dangling_bounded_block_data[%s_%s]" % (dangle.name, comp), "dangle", (comp, dangle)))
 
+        if profile == "hq":
+            variants.append(("lossless_quantization", "lossless_q", ()))
+
         for vname, kind, args in variants:
             t = copy.deepcopy(td)
+            pv, statev = p, state
+            if kind == "lossless_q":
+                # lossless_quantization (test_cases/decoder/lossless_quantization.py:117-190): a lossless picture
+                # whose every coefficient is 1 at a qindex high enough for all quantisation factors to differ
+                # (largest matrix entry + MINIMUM_DISTINCT_QINDEX), length fields from the reference's
+                # calculate_hq_length_field, slice_size_scaler raised until they fit eight bits.
+                _scaler0, t = encp.make_transform_data_hq_lossless(slice_coeffs)
+                qi = max(v for sub in qm.values() for v in sub.values()) + tcl.MINIMUM_DISTINCT_QINDEX
+                longest = 0
+                for sl in t[key]:
+                    sl["qindex"] = qi
+                    for c in ("y", "c1", "c2"):
+                        sl[c + "_transform"] = [1] * len(sl[c + "_transform"])
+                        sl["slice_%s_length" % c] = encp.calculate_hq_length_field(sl[c + "_transform"], 1)
+                        longest = max(longest, sl["slice_%s_length" % c])
+                new_scaler = max(1, (longest + 254) // 255)
+                for sl in t[key]:
+                    for c in ("y", "c1", "c2"):
+                        sl["slice_%s_length" % c] = (sl["slice_%s_length" % c] + new_scaler - 1) // new_scaler
+                pv = O.make_params(W, H, W // cdiv[0], H // cdiv[1], depth, depth, wi, wiho, d, dho, sx, sy,
+                                   False, 0, new_scaler, 0, 1, qm)
+                statev = MG.state_from_params(pv, qm)
+                rec["%s.%s.params" % (name, vname)] = MG.params_to_array(pv)
             try:
                 for n, sl in enumerate(t[key]):
                     sy_, sx_ = divmod(n, sx)
+                    if kind == "lossless_q":
+                        break
                     if kind == "pad" and profile == "hq":
                         tcp.fill_hq_slice_padding(state, sx_, sy_, sl, args[0], args[1], args[2])
                     elif kind == "pad":
@@ -119,10 +149,12 @@ def main():
             except tcp.UnsatisfiableBlockSizeError:
                 print("   (slices too small for %s %s)" % (name, vname))
                 continue
-            data = MG.serialise_transform_data(t, state)
-            res = MG.ref_decode(p, qm, data + b"\x00")
+            data = MG.serialise_transform_data(t, statev)
+            res = MG.ref_decode(pv, qm, data + b"\x00")
             assert res["status"] == 0 and res["consumed"] == len(data), (name, vname, res.get("consumed"), len(data))
-            MG.check_oracle_decode(p, data + b"\x00", res, name + "." + vname)
+            MG.check_oracle_decode(pv, data + b"\x00", res, name + "." + vname)
+            if kind == "lossless_q":  # the generator drops pictures that clip (:176-190)
+                assert all(0 < int(a.min()) and int(a.max()) < (1 << depth) - 1 for a in res["picture"]), name
             full = "%s.%s" % (name, vname)
             rec[full + ".data"] = np.frombuffer(data, np.uint8)
             for c in range(3):
