@@ -345,8 +345,9 @@ __device__ __forceinline__ long long hq_total_length(const DevParams &P, const F
     return ((n + 1) * F.total_coeff_bytes) / den - (n * F.total_coeff_bytes) / den;
 }
 
-// last qindex found for a picture (search hint shared by the warps of that picture; stale or racy
-// values only cost probes)
+// last qindex found for a picture: the search hint of a warp's FIRST slice (shared by the warps of that
+// picture; stale or racy values only cost probes).  Later slices start from the warp's own previous answer
+// -- the slice next door -- which costs no dependent global load.
 constexpr int kHintSlots = 1024;
 __device__ int g_qindex_hint[kHintSlots];
 
@@ -444,8 +445,17 @@ quantize_fit_kernel(DevParams P, FitArgs F, const int32_t *__restrict__ coeffs, 
     }
     __syncthreads();
 
-  for (long long gw = (long long)blockIdx.x * kQWarps + warp; gw < total_slices; gw += (long long)gridDim.x * kQWarps) {
+  // A warp walks a contiguous run of slices, so its previous answer is the answer of the slice next door.
+  // (Fetching the next slice's coefficients by cp.async behind the current search was tried and lost:
+  // 163 against 150 us per 2160p picture -- the extra staging buffer costs a resident CTA per SM.)
+  int own_hint = -1;
+  const long long nwarps_total = (long long)gridDim.x * kQWarps;
+  const long long run = (total_slices + nwarps_total - 1) / nwarps_total;
+  const long long gw0 = ((long long)blockIdx.x * kQWarps + warp) * run;
+  for (long long gw = gw0; gw < min(gw0 + run, total_slices); gw++) {
     const int pic = (int)(gw / nslices);
+    // issued before the staging loads so that its latency hides behind them
+    const int shared_hint = own_hint < 0 ? g_qindex_hint[pic & (kHintSlots - 1)] : 0;
     const int n = (int)(gw - (long long)pic * nslices);
     const int sy = n / P.slices_x, sx = n - sy * P.slices_x;
     const int32_t *pc = coeffs + (size_t)pic * P.pic_coeffs;
@@ -536,7 +546,7 @@ quantize_fit_kernel(DevParams P, FitArgs F, const int32_t *__restrict__ coeffs, 
         // Neighbouring slices of a picture usually need almost the same index: gallop outwards from
         // the last answer any warp published for this picture (a hint only -- every bound used
         // below is established by an actual probe), then bisect the bracket.
-        const int hint = g_qindex_hint[pic & (kHintSlots - 1)];
+        const int hint = own_hint < 0 ? shared_hint : own_hint;
         if (hint > lo && hint < hi) {
             if (fits(hint)) {
                 hi = hint;
@@ -554,7 +564,8 @@ quantize_fit_kernel(DevParams P, FitArgs F, const int32_t *__restrict__ coeffs, 
             const int mid = (lo + hi) >> 1;
             if (fits(mid)) hi = mid; else lo = mid + 1;
         }
-        if (lane == 0) g_qindex_hint[pic & (kHintSlots - 1)] = lo;
+        if (lane == 0 && own_hint < 0) g_qindex_hint[pic & (kHintSlots - 1)] = lo;
+        own_hint = lo;
     }
     if (ok_q == lo) { by = oy; bc1 = o1; bc2 = o2; }  // the answer is the last probe that fitted
     else fits(lo);
@@ -815,7 +826,7 @@ int vc2b_quantize_to_fit(const vc2b_params *p, const int32_t *d_coeffs, int npic
         if (attr != cudaSuccess) return (int)attr;
     }
     const long long warps = npictures * nslices;
-    // persistent CTAs: each warp walks slices gw, gw + grid * kQWarps, ... (the reference map is built once per CTA)
+    // persistent CTAs: each warp walks a contiguous run of slices (the reference map is built once per CTA)
     long long nblk = (warps + kQWarps - 1) / kQWarps;
     if (nblk > 148LL * 16) nblk = 148LL * 16;
     quantize_fit_kernel<<<(unsigned)nblk, kQWarps * 32, smem, (cudaStream_t)stream>>>(
