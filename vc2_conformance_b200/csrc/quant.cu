@@ -361,6 +361,49 @@ struct FitMap {
     int32_t ny, nc, ok;
 };
 
+// Builds the map from slice (0, 0) with all threads of the CTA (tabs: two scratch SliceBands of warp 0).
+// `limit`: the map is only used when the reference slice has at most that many coefficients per picture.
+__device__ __forceinline__ void build_fit_map(const DevParams &P, FitMap &M, SliceBands *tabs0, bool enable, int limit)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (warp == 0) {
+        const int ny0 = build_slice_bands(P, 0, 0, 0, tabs0[0], lane);
+        const int nc0 = build_slice_bands(P, 1, 0, 0, tabs0[1], lane);
+        if (lane < P.nb) {
+            for (int k = 0; k < 2; k++) {
+                M.ref_w[k][lane] = tabs0[k].w[lane];
+                M.ref_cnt[k][lane] = tabs0[k].cum[lane + 1] - tabs0[k].cum[lane];
+            }
+        }
+        if (lane == 0) {
+            M.ny = ny0;
+            M.nc = nc0;
+            M.ok = enable && (ny0 + nc0 <= kStageMax) && (ny0 + 2 * nc0 <= limit);
+        }
+    }
+    __syncthreads();
+    if (M.ok) {
+        for (int j = threadIdx.x; j < M.ny + M.nc; j += blockDim.x) {
+            const SliceBands &T = j < M.ny ? tabs0[0] : tabs0[1];
+            int b;
+            const int off = locate_coeff(T, P.nb, j < M.ny ? j : j - M.ny, &b);
+            M.e[j] = ((uint32_t)b << 24) | (uint32_t)(off - T.base[b]);
+        }
+    }
+    __syncthreads();
+}
+
+// whether the slice described by TY / TC has the rectangles of the reference slice (warp-uniform)
+__device__ __forceinline__ bool matches_fit_map(const DevParams &P, const FitMap &M, const SliceBands &TY,
+                                                const SliceBands &TC, int lane)
+{
+    bool same = M.ok != 0;
+    if (same && lane < P.nb)
+        same = TY.w[lane] == M.ref_w[0][lane] && TY.cum[lane + 1] - TY.cum[lane] == M.ref_cnt[0][lane] &&
+               TC.w[lane] == M.ref_w[1][lane] && TC.cum[lane + 1] - TC.cum[lane] == M.ref_cnt[1][lane];
+    return __all_sync(0xffffffffu, same);
+}
+
 // stage one (NSRC = 1) or two (C1 and C2, same geometry) components through the map: dst[j * step] for
 // j < n.  Sixteen loads per lane are issued before the first one is used: a slice is a few hundred
 // scattered 8..64-byte row segments, and the stage is bound by their latency, not by bandwidth.
@@ -418,32 +461,7 @@ quantize_fit_kernel(DevParams P, FitArgs F, const int32_t *__restrict__ coeffs, 
     const int nslices = P.slices_x * P.slices_y;
     const long long total_slices = (long long)npictures * nslices;
 
-    // reference map from slice (0, 0)
-    if (warp == 0) {
-        const int ny0 = build_slice_bands(P, 0, 0, 0, tabs[0][0], lane);
-        const int nc0 = build_slice_bands(P, 1, 0, 0, tabs[0][1], lane);
-        if (lane < P.nb) {
-            for (int k = 0; k < 2; k++) {
-                M.ref_w[k][lane] = tabs[0][k].w[lane];
-                M.ref_cnt[k][lane] = tabs[0][k].cum[lane + 1] - tabs[0][k].cum[lane];
-            }
-        }
-        if (lane == 0) {
-            M.ny = ny0;
-            M.nc = nc0;
-            M.ok = F.use_map && (ny0 + nc0 <= kStageMax) && (ny0 + 2 * nc0 <= F.stage_cap);
-        }
-    }
-    __syncthreads();
-    if (M.ok) {
-        for (int j = threadIdx.x; j < M.ny + M.nc; j += kQWarps * 32) {
-            const SliceBands &T = j < M.ny ? tabs[0][0] : tabs[0][1];
-            int b;
-            const int off = locate_coeff(T, P.nb, j < M.ny ? j : j - M.ny, &b);
-            M.e[j] = ((uint32_t)b << 24) | (uint32_t)(off - T.base[b]);
-        }
-    }
-    __syncthreads();
+    build_fit_map(P, M, tabs[0], F.use_map != 0, F.stage_cap);
 
   // A warp walks a contiguous run of slices, so its previous answer is the answer of the slice next door.
   // (Fetching the next slice's coefficients by cp.async behind the current search was tried and lost:
@@ -468,12 +486,8 @@ quantize_fit_kernel(DevParams P, FitArgs F, const int32_t *__restrict__ coeffs, 
     // fast path: slice staged as 4|c| in shared memory, every magnitude below kFastMagLimit
     bool staged = (ny + 2 * nc) <= F.stage_cap;
     if (staged) {
-        bool same = M.ok != 0;
-        if (same && lane < P.nb)
-            same = TY.w[lane] == M.ref_w[0][lane] && TY.cum[lane + 1] - TY.cum[lane] == M.ref_cnt[0][lane] &&
-                   TC.w[lane] == M.ref_w[1][lane] && TC.cum[lane + 1] - TC.cum[lane] == M.ref_cnt[1][lane];
         uint32_t mx;
-        if (__all_sync(0xffffffffu, same)) {
+        if (matches_fit_map(P, M, TY, TC, lane)) {
             const int32_t *c0 = pc + P.comp_off[0], *c1 = pc + P.comp_off[1], *c2 = pc + P.comp_off[2];
             mx = stage_mapped<1>(M.e, TY, c0, nullptr, ny, S.coef, S.band, nullptr, nullptr, 1, lane);
             if (P.is_ld)
@@ -599,6 +613,13 @@ __device__ __forceinline__ void put_bits(uint32_t *__restrict__ out32, long long
     if (len <= 0) return;
     const long long w0 = pos >> 5;
     const int o = (int)(pos & 31);
+    if (len <= 32) {  // the usual case: at most two words
+        const unsigned long long t = (code & 0xffffffffull) << (64 - o - len);
+        const uint32_t q0 = (uint32_t)(t >> 32), q1 = (uint32_t)t;
+        if (q0) atomicOr(&out32[w0], __byte_perm(q0, 0, 0x0123));
+        if (q1) atomicOr(&out32[w0 + 1], __byte_perm(q1, 0, 0x0123));
+        return;
+    }
     // 96-bit window [w0, w0+3): place the code so that its MSB sits at bit offset o
     const int sh = 96 - o - len;  // >= 0
     uint32_t p0 = 0, p1 = 0, p2 = 0;
@@ -624,6 +645,17 @@ __device__ __forceinline__ unsigned long long sint_code(int32_t v, int *len)
 {
     if (v == 0) { *len = 1; return 1ull; }
     const uint32_t mag = v < 0 ? (uint32_t)(-(long long)v) : (uint32_t)v;
+    if (mag < 0x7fffu) {  // at most 14 data bits: the code fits 30 bits, all in 32-bit arithmetic
+        const uint32_t m32 = mag + 1;
+        const int k32 = 31 - __clz(m32);
+        uint32_t d32 = m32 - (1u << k32);
+        d32 = (d32 | (d32 << 8)) & 0x00ff00ffu;
+        d32 = (d32 | (d32 << 4)) & 0x0f0f0f0fu;
+        d32 = (d32 | (d32 << 2)) & 0x33333333u;
+        d32 = (d32 | (d32 << 1)) & 0x55555555u;
+        *len = 2 * k32 + 2;
+        return (unsigned long long)((((d32 << 1) | 1u) << 1) | (v < 0 ? 1u : 0u));
+    }
     const unsigned long long m = (unsigned long long)mag + 1;
     const int k = 63 - __clzll((long long)m);
     unsigned long long d = m - (1ull << k);  // k data bits
@@ -642,12 +674,22 @@ __device__ __forceinline__ unsigned long long sint_code(int32_t v, int *len)
 template <bool INTERLEAVED>
 __device__ void pack_block(const SliceBands &T, int nb, const int32_t *__restrict__ c1,
                            const int32_t *__restrict__ c2, int ncoef, const uint2 *qtab, uint32_t *__restrict__ out32,
-                           long long start, long long end, int lane)
+                           long long start, long long end, int lane, const uint32_t *map)
 {
+    // map: the CTA's coefficient -> (band, offset) table for this component when the slice has the
+    // reference rectangles (build_fit_map), else nullptr (band search and division per coefficient)
     auto fetch = [&](int idx, int *band) -> int32_t {
         if (idx >= ncoef) { *band = 0; return 0; }
         const int j = INTERLEAVED ? (idx >> 1) : idx;
-        return __ldg(((INTERLEAVED && (idx & 1)) ? c2 : c1) + locate_coeff(T, nb, j, band));
+        int off;
+        if (map) {
+            const uint32_t e = map[j];
+            *band = (int)(e >> 24);
+            off = T.base[*band] + (int)(e & 0xffffffu);
+        } else {
+            off = locate_coeff(T, nb, j, band);
+        }
+        return __ldg(((INTERLEAVED && (idx & 1)) ? c2 : c1) + off);
     };
     long long pos = start;
     int bn;
@@ -681,10 +723,17 @@ pack_slices_kernel(DevParams P, FitArgs F, const int32_t *__restrict__ coeffs, i
 {
     __shared__ SliceBands tabs[kQWarps][2];
     __shared__ uint2 qtabs[kQWarps][kMaxBands];  // {qf saturated to 2^32-1, floor((2^32-1) / qf)} per band
+    __shared__ FitMap M;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nslices = P.slices_x * P.slices_y;
-    const long long gw = (long long)blockIdx.x * kQWarps + warp;
-    if (gw >= (long long)npictures * nslices) return;
+    const long long total_slices = (long long)npictures * nslices;
+    build_fit_map(P, M, tabs[0], F.use_map != 0, kStageMax);
+
+  // persistent CTAs, a contiguous run of slices per warp (as in quantize_fit_kernel)
+  const long long nwarps_total = (long long)gridDim.x * kQWarps;
+  const long long run = (total_slices + nwarps_total - 1) / nwarps_total;
+  const long long gw0 = ((long long)blockIdx.x * kQWarps + warp) * run;
+  for (long long gw = gw0; gw < min(gw0 + run, total_slices); gw++) {
     const int pic = (int)(gw / nslices);
     const int n = (int)(gw - (long long)pic * nslices);
     const int sy = n / P.slices_x, sx = n - sy * P.slices_x;
@@ -692,8 +741,11 @@ pack_slices_kernel(DevParams P, FitArgs F, const int32_t *__restrict__ coeffs, i
     SliceBands &TY = tabs[warp][0];
     SliceBands &TC = tabs[warp][1];
     const uint2 *qtab = qtabs[warp];
+    __syncwarp();
     const int ny = build_slice_bands(P, 0, sx, sy, TY, lane);
     const int nc = build_slice_bands(P, 1, sx, sy, TC, lane);
+    const bool mapped = matches_fit_map(P, M, TY, TC, lane);
+    const uint32_t *map_y = mapped ? M.e : nullptr, *map_c = mapped ? M.e + ny : nullptr;
     const int qindex = qindex_in[gw];
     stage_pack_quantisers(TY, P.nb, qindex, qtabs[warp], lane);  // quant matrices are identical for the components
     uint32_t *out32 = reinterpret_cast<uint32_t *>(out);  // out is 4-byte aligned; positions absolute
@@ -712,9 +764,9 @@ pack_slices_kernel(DevParams P, FitArgs F, const int32_t *__restrict__ coeffs, i
             put_bits(out32, pos + 7, (unsigned long long)y_len, length_bits, end);
         }
         pos += 7 + length_bits;
-        pack_block<false>(TY, P.nb, pc + P.comp_off[0], nullptr, ny, qtab, out32, pos, pos + y_len, lane);
+        pack_block<false>(TY, P.nb, pc + P.comp_off[0], nullptr, ny, qtab, out32, pos, pos + y_len, lane, map_y);
         pos += y_len;
-        pack_block<true>(TC, P.nb, pc + P.comp_off[1], pc + P.comp_off[2], 2 * nc, qtab, out32, pos, end, lane);
+        pack_block<true>(TC, P.nb, pc + P.comp_off[1], pc + P.comp_off[2], 2 * nc, qtab, out32, pos, end, lane, map_c);
     } else {
         // hq_slice (bitstream/vc2.py:798): prefix bytes (zero), qindex, then per component a
         // length byte and a bounded block of 8*scaler*length bits (make_hq_slice :456)
@@ -733,16 +785,17 @@ pack_slices_kernel(DevParams P, FitArgs F, const int32_t *__restrict__ coeffs, i
             put_bits(out32, pos + 8, (unsigned long long)ly, 8, big);
         }
         pos += 16;
-        pack_block<false>(TY, P.nb, pc + P.comp_off[0], nullptr, ny, qtab, out32, pos, pos + align * ly, lane);
+        pack_block<false>(TY, P.nb, pc + P.comp_off[0], nullptr, ny, qtab, out32, pos, pos + align * ly, lane, map_y);
         pos += align * ly;
         if (lane == 0) put_bits(out32, pos, (unsigned long long)l1, 8, big);
         pos += 8;
-        pack_block<false>(TC, P.nb, pc + P.comp_off[1], nullptr, nc, qtab, out32, pos, pos + align * l1, lane);
+        pack_block<false>(TC, P.nb, pc + P.comp_off[1], nullptr, nc, qtab, out32, pos, pos + align * l1, lane, map_c);
         pos += align * l1;
         if (lane == 0) put_bits(out32, pos, (unsigned long long)l2, 8, big);
         pos += 8;
-        pack_block<false>(TC, P.nb, pc + P.comp_off[2], nullptr, nc, qtab, out32, pos, pos + align * l2, lane);
+        pack_block<false>(TC, P.nb, pc + P.comp_off[2], nullptr, nc, qtab, out32, pos, pos + align * l2, lane, map_c);
     }
+  }  // slices of this warp
 }
 
 static int max_qm(const DevParams &P)
@@ -870,12 +923,17 @@ int vc2b_pack_slices(const vc2b_params *p, const int32_t *d_coeffs, int npicture
     F.minimum_qindex = 0;
     F.max_qm = max_qm(P);
     F.stage_cap = 0;
-    F.use_map = 0;
+    F.use_map = 1;
+    for (int c = 0; c < 3; c++)
+        for (int b = 0; b < P.nb; b++)
+            if ((long long)P.band[c][b].w * P.band[c][b].h >= (1 << 24)) F.use_map = 0;
     cudaStream_t s = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(d_out, 0, (size_t)out_stride * npictures, s);
     if (e != cudaSuccess) return (int)e;
     const long long warps = npictures * nslices;
-    pack_slices_kernel<<<(unsigned)((warps + kQWarps - 1) / kQWarps), kQWarps * 32, 0, s>>>(
+    long long nblk = (warps + kQWarps - 1) / kQWarps;
+    if (nblk > 148LL * 16) nblk = 148LL * 16;  // persistent CTAs (the reference map is built once per CTA)
+    pack_slices_kernel<<<(unsigned)nblk, kQWarps * 32, 0, s>>>(
         P, F, d_coeffs, npictures, d_qindex, d_slice_bits, d_out, out_stride);
     VC2B_CHECK_LAUNCH();
     return 0;
