@@ -396,8 +396,18 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = "cuda:%d" % local_rank
+    numa_cpus = 0
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
+        if not os.environ.get("VC2B_NO_NUMA_BIND"):
+            # one process per GPU: keep the pinned host buffers of this rank in the GPU's NUMA node
+            from vc2_conformance_b200.sharding import bind_process_to_gpu
+
+            try:
+                uuid0 = torch.cuda.get_device_properties(local_rank).uuid
+            except Exception:
+                uuid0 = None
+            numa_cpus = bind_process_to_gpu(local_rank, uuid0)
 
     w = make_workload(args.workload, args.pictures)
     p = w["p"]
@@ -523,6 +533,7 @@ def run_ours(args):
             "d2h_bytes_per_step": int(2 * S * NP),
             "gpu_launches": seq.launches - l0,
             "pipeline": "%d-picture chunks over 3 CUDA streams" % chunk,
+            "numa_bound_cpus": numa_cpus,
         }
     sampler.stop()
     clocks = sampler.summary(clock_windows)

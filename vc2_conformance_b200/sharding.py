@@ -40,3 +40,37 @@ def gather_counts(local_count):
     t = torch.tensor([int(local_count)], dtype=torch.int64)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return int(t.item())
+
+
+def bind_process_to_gpu(device_index, uuid=None):
+    """Restricts this process to the CPUs NVML reports as local to the GPU (its NUMA node), so that the
+    pinned host buffers allocated afterwards live in that node's memory and the host<->device copies of
+    different ranks do not all cross the same socket interconnect.  One process per GPU; call it before
+    allocating pinned memory.  Returns the number of CPUs bound to, 0 if nothing was changed (NVML or the
+    affinity call unavailable)."""
+    import os
+
+    try:
+        import pynvml as N
+
+        N.nvmlInit()
+        h = None
+        if uuid:
+            try:
+                h = N.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+            except Exception:
+                h = None
+        if h is None:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = int(vis.split(",")[device_index]) if vis else device_index
+            h = N.nvmlDeviceGetHandleByIndex(idx)
+        ncpu = os.cpu_count() or 1
+        mask = N.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        allowed = os.sched_getaffinity(0)
+        cpus = {i for i in range(ncpu) if (mask[i // 64] >> (i % 64)) & 1} & allowed
+        if not cpus or cpus == allowed:
+            return 0
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
