@@ -759,7 +759,11 @@ __device__ __forceinline__ int narrow_or_flag(long long v, int *maxabs)
 // barrier on the chain.  The warps of a CTA are pipelined down the band: lane 0 of warp b reads the row
 // above (the last row of warp b-1) back from global memory, eight groups ahead, once warp b-1 has
 // published (fence + a shared progress word) that it is written; in steady state the producer is 31
-// steps ahead and nobody spins.  Own rows are prefetched eight steps ahead into a register ring.
+// steps ahead and nobody spins.  Own rows are staged eight steps ahead by cp.async.
+// Measured (64 1080i fields, 202 us): without the stores 124 us, without the dependent chain 87 us.  What
+// binds the kernel is the L1TEX pipe: every lane of a warp touches a different row, so each 16-byte
+// load / store instruction is 32 separate wavefronts (about 64 per warp and step, 16 warps per SM).  A
+// skewed scratch layout S[x + y][y] would make the wavefront's accesses contiguous (next step).
 constexpr int kDcWarps = 8;      // rows per pass = 32 * kDcWarps
 constexpr int kDcAhead = 8;      // groups prefetched ahead (register ring; loop unrolled by it)
 
@@ -936,7 +940,9 @@ dc_prediction_fwd_kernel(DevParams P, int32_t *__restrict__ coeffs, int32_t *__r
                             if (x0 + 2 < w) row[x0 + 2] = out.z;
                             if (x0 + 3 < w) row[x0 + 3] = out.w;
                         }
-                        if (lane == 31) {  // the next warp's row above: publish
+                        // the next warp's row above: published once per block of kDcAhead steps (a fence per
+                        // step waits for the lane's stores on the critical path)
+                        if (lane == 31 && (u == kDcAhead - 1 || g == ngroups - 1)) {
                             __threadfence_block();
                             progress[wb] = g + 1;
                         }
