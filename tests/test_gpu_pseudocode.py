@@ -251,3 +251,31 @@ def test_fragmented_picture_path(name):
     P.picture_decode(st)
     for c, key in enumerate(["Y", "C1", "C2"]):
         assert (np.array(got[0][key]) == z[name + ".decoded%d" % c]).all(), (name, key)
+
+
+@pytest.mark.parametrize("w,h,mag", [
+    (480, 135, 1 << 10),        # BASELINE config 3 DC band: five pipelined warps
+    (64, 300, 1 << 20),         # taller than one pass of 256 rows: the row above comes from the previous pass
+    (37, 70, 1 << 27),          # width not a multiple of four (scalar edge path), just below the 2^28 fast-path bound
+    (40, 40, (1 << 28) + 5),    # operands beyond the 32-bit fast path: groups redone exactly in 64 bits
+    (16, 33, (1 << 30) - 1),
+    (4, 1, 100), (1, 40, 100),  # single row / single column
+])
+def test_dc_prediction_magnitudes_and_shapes(w, h, mag):
+    """dc_prediction_fwd_kernel against the oracle: the 32-bit biased mean is only used while every
+    operand is within +-2^28 (dc_group), larger values take the exact path; warps of a CTA hand rows
+    over through global memory, passes of 256 rows through a block barrier."""
+    import oracle as O
+    from vc2_conformance_b200 import pseudocode as P
+
+    rng = np.random.RandomState(w * 1000 + h)
+    # residues small enough for the prediction sums to stay inside int32 (the envelope flag is tested elsewhere)
+    band = rng.randint(-mag // 64 - 1, mag // 64 + 2, (h, w)).astype(np.int64)
+    band[0, 0] = mag // 2
+    band[h // 2, w // 2] = -(mag // 2)
+    want = O.dc_prediction(band)
+    if int(np.abs(want).max()) >= (1 << 31):
+        pytest.skip("prediction leaves int32 for this seed")
+    got = band.tolist()
+    P.dc_prediction(got)
+    assert (np.array(got, dtype=np.int64) == want).all()

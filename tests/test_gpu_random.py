@@ -294,3 +294,53 @@ def test_idwt_fused_levels(case, monkeypatch):
             planes = codec.picture_planes(i)
             for c in range(3):
                 assert (planes[c] == decoded[i][c]).all(), (case, fused, i, c)
+
+
+@pytest.mark.parametrize("mag_bits", [12, 27, 28, 29, 30])
+@pytest.mark.parametrize("is_ld", [False, True])
+def test_quantiser_search_and_packer_on_large_coefficients(mag_bits, is_ld):
+    """quantize_fit_kernel's division-free probe is only valid for |c| < 2^28 (kFastMagLimit): slices with
+    larger magnitudes must take the exact path, and pack_slices_kernel's 32-bit code builder must hand
+    over to the 64-bit one for long codes.  Coefficients are written straight into the codec's
+    coefficient buffer; bytes and qindex must equal the oracle's."""
+    import oracle as O
+    from vc2_conformance_b200.device import BatchCodec
+
+    if is_ld and mag_bits >= 30:
+        pytest.skip("the DC prediction residues of 2^30 magnitudes leave int32 (envelope flag, tested elsewhere)")
+    W, H, sx, sy = 64, 32, 4, 4
+    S = W * H * 2
+    picture_bytes = S // 2
+    kw = dict(luma_width=W, luma_height=H, color_diff_width=W // 2, color_diff_height=H, luma_depth=10,
+              wavelet_index=1, dwt_depth=2, slices_x=sx, slices_y=sy)
+    if is_ld:
+        kw.update(is_ld=True, slice_bytes_numerator=picture_bytes, slice_bytes_denominator=sx * sy)
+    else:
+        kw.update(slice_size_scaler=O.safe_lossy_hq_slice_size_scaler(picture_bytes, sx * sy))
+    p = _mk(**kw)
+    po = synth.oracle_params(p)
+    codec = BatchCodec(p, 2)
+    g = codec.g
+    rng = np.random.RandomState(mag_bits)
+    lim = (1 << mag_bits) - 1
+    comps_all = []
+    for i in range(2):
+        comps = [rng.randint(-lim, lim + 1, n).astype(np.int64) for n in g.comp_coeffs]
+        if i == 1:  # mostly small values with a few large ones: some slices fast, some exact
+            comps = [np.where(rng.rand(c.size) < 0.02, c, c % 7 - 3) for c in comps]
+        comps_all.append(comps)
+        flat = np.concatenate(comps).astype(np.int32)
+        codec.coeffs[i * g.picture_coeffs:(i + 1) * g.picture_coeffs].copy_(codec.torch.from_numpy(flat))
+    codec.quantize_device(2, 0 if is_ld else picture_bytes)
+    out, nbytes = codec.pack_device(2, 0 if is_ld else picture_bytes)
+    got = out.cpu().numpy()
+    qi = codec.qindex[: 2 * sx * sy].cpu().numpy().reshape(2, -1)
+    for i in range(2):
+        comps = comps_all[i]
+        if is_ld:
+            # the oracle's LD encoder applies the DC prediction itself; quantize_device did so in place
+            want, wq = O.encode_ld_lossy(po, comps)
+        else:
+            want, wq = O.encode_hq_lossy(po, comps, picture_bytes)
+        assert (qi[i] == wq).all(), (mag_bits, is_ld, i)
+        assert got[i, :nbytes].tobytes() == want, (mag_bits, is_ld, i)
