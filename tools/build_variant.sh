@@ -7,4 +7,5 @@ name=$1; shift
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr \
   -DVC2B_DEV_BUILD "$@" -Xptxas -v -c csrc/idwt.cu -o _lib/variant_$name.o 2> _lib/variant_$name.ptxas
 grep -A2 "fused2" _lib/variant_$name.ptxas | grep -E "Used|spill" | head -2
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o _lib/variant_$name.so _lib/variant_$name.o _lib/dwt.o _lib/params.o _lib/quant.o _lib/unpack.o
+others=$(ls _lib/*.o | grep -v -e '_lib/idwt.o' -e '_lib/variant_')
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o _lib/variant_$name.so _lib/variant_$name.o $others
