@@ -45,7 +45,7 @@ __device__ __forceinline__ int4 *ring_slot(int4 *ring, int m, int lane)
     return ring + ((m & (RS - 1)) * 4) * 32 + lane;
 }
 
-template <int RS>
+template <int RS, bool COMMIT = true>
 __device__ __forceinline__ void ring_stage_pair(const Strip8Ctx &X, int4 *ring, int m)
 {
     const int sy = min(max(m, 0), X.h - 1);
@@ -55,7 +55,7 @@ __device__ __forceinline__ void ring_stage_pair(const Strip8Ctx &X, int4 *ring, 
     cp_async_vec(st + 32, X.b0 + idx);
     cp_async_vec(st + 64, X.b1 + idx);
     cp_async_vec(st + 96, X.b2 + idx);
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (COMMIT) asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
 // One lifting stage of one step: updates the row of parity `par` of pair k from the rows of the other
@@ -128,6 +128,64 @@ __device__ __forceinline__ void ring_vstage(int4 *ring, int lane, int t, int las
     }
 }
 
+// The same stage for TWO consecutive steps (pairs k and k + 1) at once.  Within a stage the updates of
+// different pairs are independent (a stage only reads the other row parity), and running stage s of step
+// t + 1 before stage s + 1 of step t changes nothing either: stage s + 1 at step t reads pairs that stage
+// s finished at step t or earlier, and writes a pair that stage s has already read (that is what the
+// lags of the streaming plan guarantee).  The two windows overlap in L - 1 of L source rows, so a block
+// of two steps loads L + 1 rows instead of 2 L -- the kernel is bound by shared-memory traffic and by
+// the latency of these loads -- and the two accumulations interleave.
+template <int FV, int SIDX, int RS>
+__device__ __forceinline__ void ring_vstage2(int4 *ring, int lane, int t, int last)
+{
+    constexpr StreamPlan P = make_stream_plan(FV);
+    constexpr StageDef st = stream_stage(FV, SIDX, false);
+    constexpr int par = P.parity[SIDX];
+    constexpr bool add = (st.type == 1 || st.type == 3);
+    constexpr int L = st.L;
+    using Acc = typename std::conditional<(st.S >= kWideAccS), long long, int>::type;
+    const int k = t - P.lag[SIDX];
+    if (k < 0 || k + 1 > last || k + P.dmin[SIDX] < 0 || k + 1 + P.dmax[SIDX] > last) {
+        // a clamped window (picture top / bottom) or a pair outside the picture: one step at a time
+        ring_vstage<FV, SIDX, RS>(ring, lane, t, last);
+        ring_vstage<FV, SIDX, RS>(ring, lane, t + 1, last);
+        return;
+    }
+    constexpr Acc rnd = st.S > 0 ? (Acc)1 << (st.S > 0 ? st.S - 1 : 0) : (Acc)0;
+#pragma unroll
+    for (int v = 0; v < 2; v++) {
+        int4 a[L + 1];
+#pragma unroll
+        for (int i = 0; i <= L; i++) a[i] = ring_slot<RS>(ring, k + P.dmin[SIDX] + i, lane)[(2 * (1 - par) + v) * 32];
+        Acc s0[4] = {rnd, rnd, rnd, rnd}, s1[4] = {rnd, rnd, rnd, rnd};
+#pragma unroll
+        for (int i = 0; i < L; i++) {
+            s0[0] += (Acc)st.taps[i] * (Acc)a[i].x;
+            s0[1] += (Acc)st.taps[i] * (Acc)a[i].y;
+            s0[2] += (Acc)st.taps[i] * (Acc)a[i].z;
+            s0[3] += (Acc)st.taps[i] * (Acc)a[i].w;
+            s1[0] += (Acc)st.taps[i] * (Acc)a[i + 1].x;
+            s1[1] += (Acc)st.taps[i] * (Acc)a[i + 1].y;
+            s1[2] += (Acc)st.taps[i] * (Acc)a[i + 1].z;
+            s1[3] += (Acc)st.taps[i] * (Acc)a[i + 1].w;
+        }
+        int4 *tp0 = ring_slot<RS>(ring, k, lane) + (2 * par + v) * 32;
+        int4 *tp1 = ring_slot<RS>(ring, k + 1, lane) + (2 * par + v) * 32;
+        int4 v0 = *tp0, v1 = *tp1;
+        const int d0[4] = {(int)(s0[0] >> st.S), (int)(s0[1] >> st.S), (int)(s0[2] >> st.S), (int)(s0[3] >> st.S)};
+        const int d1[4] = {(int)(s1[0] >> st.S), (int)(s1[1] >> st.S), (int)(s1[2] >> st.S), (int)(s1[3] >> st.S)};
+        if (add) {
+            v0.x += d0[0]; v0.y += d0[1]; v0.z += d0[2]; v0.w += d0[3];
+            v1.x += d1[0]; v1.y += d1[1]; v1.z += d1[2]; v1.w += d1[3];
+        } else {
+            v0.x -= d0[0]; v0.y -= d0[1]; v0.z -= d0[2]; v0.w -= d0[3];
+            v1.x -= d1[0]; v1.y -= d1[1]; v1.z -= d1[2]; v1.w -= d1[3];
+        }
+        *tp0 = v0;
+        *tp1 = v1;
+    }
+}
+
 template <int FV, int FH, int STEPS>
 __global__ void __launch_bounds__(32)
 idwt_ring_kernel(LevelArgs A)
@@ -180,28 +238,39 @@ idwt_ring_kernel(LevelArgs A)
     const int t_end = K1 - 1 + C::P.maxlag;
     // Pairs older than ks are never staged: whatever the slots hold only reaches rows of the warm-up
     // region (that is what `warm` is for), exactly as the zero-initialised register ring of the wide kernel.
+    // Blocks of two steps.  A block first needs its own two pairs (staged two blocks earlier), runs every
+    // stage for both steps, emits the pairs that became final, and only then stages the pairs of the block
+    // after next: their slots belong to pairs t - 12 and t - 11, which this block was the last to read.
+    static_assert(C::LOOK == 4 && (C::LIVE + C::LOOK + 1) <= RS + 1, "two-step blocks: look-ahead of two blocks");
 #pragma unroll
-    for (int u = 0; u < C::LOOK; u++) ring_stage_pair<RS>(X, ring, ks + u);
+    for (int u = 0; u < C::LOOK; u += 2) {
+        ring_stage_pair<RS, false>(X, ring, ks + u);
+        ring_stage_pair<RS, true>(X, ring, ks + u + 1);
+    }
 #pragma unroll 1
-    for (int t = ks; t <= t_end; t++) {
-        asm volatile("cp.async.wait_group %0;" ::"n"(C::LOOK - 1) : "memory");  // pair t has landed
-        ring_stage_pair<RS>(X, ring, t + C::LOOK);  // its slot held pair t + LOOK - RS, last read at step t - 1
-        ring_vstage<FV, 0, RS>(ring, X.lane, t, last);
-        if constexpr (ns > 1) ring_vstage<FV, (ns > 1 ? 1 : 0), RS>(ring, X.lane, t, last);
-        if constexpr (ns > 2) ring_vstage<FV, (ns > 2 ? 2 : 0), RS>(ring, X.lane, t, last);
-        if constexpr (ns > 3) ring_vstage<FV, (ns > 3 ? 3 : 0), RS>(ring, X.lane, t, last);
-        const int kf = t - C::P.maxlag;
-        if (kf >= K0 && kf < K1) {
-            const int4 *sl = ring_slot<RS>(ring, kf, X.lane);
+    for (int t = ks; t <= t_end; t += 2) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(C::LOOK / 2 - 1) : "memory");  // pairs t, t + 1 have landed
+        ring_vstage2<FV, 0, RS>(ring, X.lane, t, last);
+        if constexpr (ns > 1) ring_vstage2<FV, (ns > 1 ? 1 : 0), RS>(ring, X.lane, t, last);
+        if constexpr (ns > 2) ring_vstage2<FV, (ns > 2 ? 2 : 0), RS>(ring, X.lane, t, last);
+        if constexpr (ns > 3) ring_vstage2<FV, (ns > 3 ? 3 : 0), RS>(ring, X.lane, t, last);
 #pragma unroll
-            for (int par = 0; par < 2; par++) {
-                int E[NP], O[NP];
-                vec_to_array(sl[(2 * par) * 32], E);
-                vec_to_array(sl[(2 * par + 1) * 32], O);
-                if (A.final_u16) finish_row8<FH, true>(X, 2 * kf + par, E, O);
-                else finish_row8<FH, false>(X, 2 * kf + par, E, O);
+        for (int u = 0; u < 2; u++) {
+            const int kf = t + u - C::P.maxlag;
+            if (kf >= K0 && kf < K1) {
+                const int4 *sl = ring_slot<RS>(ring, kf, X.lane);
+#pragma unroll
+                for (int par = 0; par < 2; par++) {
+                    int E[NP], O[NP];
+                    vec_to_array(sl[(2 * par) * 32], E);
+                    vec_to_array(sl[(2 * par + 1) * 32], O);
+                    if (A.final_u16) finish_row8<FH, true>(X, 2 * kf + par, E, O);
+                    else finish_row8<FH, false>(X, 2 * kf + par, E, O);
+                }
             }
         }
+        ring_stage_pair<RS, false>(X, ring, t + C::LOOK);
+        ring_stage_pair<RS, true>(X, ring, t + C::LOOK + 1);
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");  // drain look-ahead copies before exit
 }
