@@ -1,4 +1,4 @@
-"""Stage micro-benchmarks (device timed): python tools/bench_stage.py idwt|dwt|unpack [--workload cfg2] [--pictures 16]"""
+"""Stage micro-benchmarks (device timed): python tools/bench_stage.py idwt|dwt|unpack|walk|quant|pack|dc|dcinv [--workload cfg2] [--pictures 16]"""
 import argparse, os, sys, ctypes as C
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
@@ -38,14 +38,20 @@ def run_unpack():
     L.vc2b_unpack(C.byref(p), _ptr(codec.data), _ptr(codec.pic_offset), NP, _ptr(codec.slice_offset), _ptr(codec.coeffs), _ptr(codec.qindex), _ptr(codec.status), sp)
 def run_walk():
     L.vc2b_hq_slice_offsets(C.byref(p), _ptr(codec.data), _ptr(codec.pic_offset), NP, _ptr(codec.slice_offset), _ptr(codec.status), sp)
+def run_dc():      # apply_dc_prediction then dc_prediction: the band returns to its values, so iterations are alike
+    L.vc2b_dc_prediction(C.byref(p), _ptr(codec.coeffs), NP, 1, sp)
+    L.vc2b_dc_prediction(C.byref(p), _ptr(codec.coeffs), NP, 0, sp)
+def run_dcinv():
+    L.vc2b_dc_prediction(C.byref(p), _ptr(codec.coeffs), NP, 1, sp)
 def run_quant():
     codec.quantize_device(NP, w["picture_bytes"])
 def run_pack():
     codec.pack_device(NP, w["picture_bytes"])
-fn = {"idwt": run_idwt, "dwt": run_dwt, "unpack": run_unpack, "walk": run_walk, "quant": run_quant, "pack": run_pack}[a.stage]
+fn = {"idwt": run_idwt, "dwt": run_dwt, "unpack": run_unpack, "walk": run_walk, "quant": run_quant, "pack": run_pack,
+      "dc": run_dc, "dcinv": run_dcinv}[a.stage]
 nbytes = {"idwt": (4 * padded + 2 * S) * NP, "dwt": (4 * padded + 2 * S) * NP,
           "unpack": int(offs[NP]) + 4 * padded * NP, "walk": int(offs[NP]), "quant": 4 * padded * NP,
-          "pack": int(offs[NP]) + 4 * padded * NP}[a.stage]
+          "pack": int(offs[NP]) + 4 * padded * NP, "dc": 0, "dcinv": 0}[a.stage]
 for _ in range(3):
     fn()
 torch.cuda.synchronize()
