@@ -502,7 +502,7 @@ static void plan_scratch(const DevParams &P, int c0, int c1, ScratchPlan *sp)
 // How many pictures' worth of intermediate LL bands the last two levels keep in flight (see run_idwt).
 // VC2B_IDWT_L2_GROUP: 0 = off (every level runs over the whole group; the default), n = fixed
 // sub-group size, -1 = as many pictures as fit kL2BudgetBytes.  Measured on B200 (cfg2, 120 pictures,
-// gpurun_out/l2_sweep.log -> profiles/): sub-groups of 1 / 4 / 12 pictures run at 51 / 33 / 28 us per
+// profiles/r1_v8_idwt_l2_subgroup_sweep.txt): sub-groups of 1 / 4 / 12 pictures run at 51 / 33 / 28 us per
 // picture against 24.9 for whole-group launches -- a sub-group is less than one wave of strips, so every
 // launch costs a full strip latency and the DRAM traffic saved does not pay for it.  Kept as an
 // experiment knob (and tested); the store hints alone are worth 3 %.
