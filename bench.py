@@ -92,6 +92,11 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--mode", default="decode", choices=["decode", "encode"],
+                    help="decode: unpack + IDWT (the headline metric); encode: DWT + quantize_to_fit + slice packing "
+                         "(BASELINE config 5: --workload cfg5 --mode encode)")
+    ap.add_argument("--no-py-reference", action="store_true",
+                    help="skip the unmodified Python reference leg of the CPU baseline (baseline/_ref)")
     ap.add_argument("--pictures", type=int, default=0, help="override pictures per sequence")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -127,15 +132,25 @@ def make_workload(name, npictures=0):
     return w
 
 
-def synth_pictures(w, first, count):
-    """Half white noise (the reference's recipe), half integer ramps, alternating."""
+def picture_kind(w, i):
+    """Picture i of a sequence: the first half white noise (the reference's recipe), the second half integer
+    ramps -- each kind a contiguous run, so that the bench can also time them separately."""
+    return "noise" if i < (w["pictures"] + 1) // 2 else "ramp"
+
+
+def synth_picture(w, rank, i):
+    import synth
+
+    seed = rank * w["pictures"] + i
+    return synth.noise_picture(w["p"], seed) if picture_kind(w, i) == "noise" else synth.ramp_picture(w["p"], seed)
+
+
+def synth_pictures(w, rank, first, count):
     import synth
 
     out = np.empty((count, w["samples"]), np.uint16)
     for i in range(count):
-        seed = first + i
-        planes = synth.noise_picture(w["p"], seed) if seed % 2 == 0 else synth.ramp_picture(w["p"], seed)
-        out[i] = synth.flat_picture(planes)
+        out[i] = synth.flat_picture(synth_picture(w, rank, first + i))
     return out
 
 
@@ -261,33 +276,63 @@ def measured_peak():
 
 
 # -------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference algorithm on host threads
+# CPU arm: the oracle port of the reference algorithm on host threads (and, where the reference tree is
+# present, the unmodified Python reference itself: tools/time_reference.py)
 # -------------------------------------------------------------------------------------------
 
-def cpu_decode_rate(w, streams, budget_s, max_threads=None):
-    """Decodes the given streams with the C oracle on all host cores (one picture per thread at
-    a time; ctypes releases the GIL).  Returns (pictures/s, cores, pictures decoded, seconds)."""
+def _oracle():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as O
+
+    O.lib()
+    return O
+
+
+def oracle_encode(O, po, w, planes):
+    coeffs = O.encode_picture(po, planes)
+    if w["p"].is_ld:
+        return O.encode_ld_lossy(po, coeffs)[0]
+    return O.encode_hq_lossy(po, coeffs, w["picture_bytes"])[0]
+
+
+def cpu_rate(w, mode, items, budget_s, check=None, max_threads=None):
+    """Runs the C oracle over ``items`` on all host cores (one picture per thread at a time; ctypes releases
+    the GIL) until ``budget_s`` has passed and every thread has finished a picture.
+    decode: items are streams, encode: items are [Y, C1, C2] planes.  ``check(i, result)`` sees the first
+    result of every item (the oracle doubling as the checker of the GPU path's output).
+    Returns (pictures/s, cores, pictures, seconds)."""
     import synth
 
+    O = _oracle()
     po = synth.oracle_params(w["p"])
-    O.lib()
     cores = max_threads or os.cpu_count() or 1
     done = [0]
     lock = threading.Lock()
+    seen = set()
     t_end = time.time() + budget_s
-    order = list(range(len(streams)))
+    errors = []
 
     def work(tid):
         k = tid
         while True:
             if time.time() > t_end and done[0] >= cores:
                 return
-            st, pics, consumed = O.decode_picture(po, streams[order[k % len(order)]])
-            assert st == 0
-            with lock:
-                done[0] += 1
+            i = k % len(items)
+            try:
+                if mode == "decode":
+                    st, res, _consumed = O.decode_picture(po, items[i])
+                    assert st == 0
+                else:
+                    res = oracle_encode(O, po, w, items[i])
+                with lock:
+                    done[0] += 1
+                    first = i not in seen
+                    seen.add(i)
+                if first and check is not None:
+                    check(i, res)
+            except Exception as e:  # noqa: BLE001 -- reported by the caller
+                errors.append(e)
+                return
             k += cores
             if time.time() > t_end:
                 return
@@ -298,49 +343,51 @@ def cpu_decode_rate(w, streams, budget_s, max_threads=None):
         t.start()
     for t in threads:
         t.join()
+    if errors:
+        raise errors[0]
     dt = time.time() - t0
     return done[0] / dt, cores, done[0], dt
 
 
-def oracle_streams(w, count):
-    """A few streams of the workload encoded by the oracle itself (CPU arm input)."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle as O
-    import synth
+def python_reference_baseline(args, mode):
+    """The unmodified Python reference on a cropped picture, one process per core (tools/time_reference.py)."""
+    if args.no_py_reference:
+        return None
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import time_reference
 
-    po = synth.oracle_params(w["p"])
-    out = []
-    for i in range(count):
-        planes = synth.noise_picture(w["p"], i) if i % 2 == 0 else synth.ramp_picture(w["p"], i)
-        coeffs = O.encode_picture(po, planes)
-        if w["p"].is_ld:
-            data, _q = O.encode_ld_lossy(po, coeffs)
-        else:
-            data, _q = O.encode_hq_lossy(po, coeffs, w["picture_bytes"])
-        out.append(data)
-    return out
+        return time_reference.measure(args.workload, (512, 256), None, mode)
+    except Exception as e:  # noqa: BLE001 -- a reported baseline must not take the GPU line down
+        return {"unavailable": "%s: %s" % (type(e).__name__, e)}
+
+
+def metric_name(mode):
+    return "decoded pictures/s" if mode == "decode" else "encoded pictures/s"
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    w = make_workload(args.workload, args.pictures)
-    # bounded sample: two distinct pictures of the workload, decoded repeatedly on all cores
-    streams = oracle_streams(w, 2)
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle as O
     import synth
 
-    O.lib()
+    w = make_workload(args.workload, args.pictures)
+    O = _oracle()
     po = synth.oracle_params(w["p"])
+    # bounded sample: two distinct pictures of the workload (one noise, one ramp), processed repeatedly
+    planes = [synth.noise_picture(w["p"], 0), synth.ramp_picture(w["p"], 1)]
+    items = planes if args.mode == "encode" else [oracle_encode(O, po, w, pl) for pl in planes]
     cores = os.cpu_count() or 1
     per_step = cores  # pictures per step: one per core
     t_steps = []
 
     def work(i):
-        st, pics, consumed = O.decode_picture(po, streams[i % len(streams)])
-        assert st == 0
+        if args.mode == "decode":
+            st, _pics, _consumed = O.decode_picture(po, items[i % len(items)])
+            assert st == 0
+        else:
+            oracle_encode(O, po, w, items[i % len(items)])
 
     for step in range(args.warmup + args.steps):
         t0 = time.time()
@@ -355,7 +402,7 @@ def run_reference(args):
     value = per_step * args.steps / total
     line = {
         "impl": "reference",
-        "metric": "decoded pictures/s",
+        "metric": metric_name(args.mode),
         "value": value,
         "unit": "pictures/s",
         "n_gpus": args.gpus,
@@ -367,11 +414,14 @@ def run_reference(args):
         "vs_baseline": None,
         "dtype": "int64",
         "data": "synthetic",
-        "config": {"workload": w["name"], "bits_per_sample": w["bits_per_sample"],
+        "config": {"workload": w["name"], "mode": args.mode, "bits_per_sample": w["bits_per_sample"],
                    "sample": "%d pictures per step (one per host core), 2 distinct pictures" % per_step},
         "cpu_baseline": {"value": value, "unit": "pictures/s", "cores": cores, "kind": "port",
-                         "sample": "%d full-size pictures per step x %d steps on %d threads"
+                         "sample": "%d full-size pictures per step x %d steps on %d threads (C restatement of the "
+                                   "reference algorithm, oracle/vc2_oracle.c; the reference itself is Python)"
                                    % (per_step, args.steps, cores)},
+        # the unmodified Python reference on a cropped picture, for scale
+        "cpu_baseline_reference": python_reference_baseline(args, args.mode),
         "e2e": {"value": value, "unit": "pictures/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -383,32 +433,87 @@ def run_reference(args):
 # GPU arm
 # -------------------------------------------------------------------------------------------
 
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
+class Rig(object):
+    """Process-level plumbing shared by the decode and encode benches: device, torch.distributed, clocks."""
 
-    from vc2_conformance_b200.device import PAD, BatchCodec, SequenceDecoder
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = "cuda:%d" % local_rank
-    numa_cpus = 0
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(dev))
-        if not os.environ.get("VC2B_NO_NUMA_BIND"):
-            # one process per GPU: keep the pinned host buffers of this rank in the GPU's NUMA node
-            from vc2_conformance_b200.sharding import bind_process_to_gpu
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = "cuda:%d" % self.local_rank
+        self.numa_cpus = 0
+        try:
+            self.uuid = torch.cuda.get_device_properties(self.local_rank).uuid
+        except Exception:
+            self.uuid = None
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device(self.dev))
+            if not os.environ.get("VC2B_NO_NUMA_BIND"):
+                # one process per GPU: keep the pinned host buffers of this rank in the GPU's NUMA node
+                from vc2_conformance_b200.sharding import bind_process_to_gpu
 
-            try:
-                uuid0 = torch.cuda.get_device_properties(local_rank).uuid
-            except Exception:
-                uuid0 = None
-            numa_cpus = bind_process_to_gpu(local_rank, uuid0)
+                self.numa_cpus = bind_process_to_gpu(self.local_rank, self.uuid)
+        self.cur = torch.cuda.current_stream()
+        self.sampler = ClockSampler(self.local_rank, self.uuid)
+        self.windows = []
 
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_ms(self, ms):
+        t = self.torch.tensor([ms], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def event(self):
+        return self.torch.cuda.Event(enable_timing=True)
+
+    def finish(self):
+        if self.world > 1:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def timed(rig, steps, warmup, step_fn, nmarks):
+    """W warm-up steps, then K steps bracketed by barrier + synchronize; ``step_fn(mark)`` calls ``mark()``
+    after each of its ``nmarks`` stages.  Returns (total ms, [mean ms per stage])."""
+    for _ in range(warmup):
+        step_fn(lambda: None)
+    rig.barrier()
+    ev = [[rig.event() for _ in range(nmarks + 1)] for _ in range(steps)]
+    e0, e1 = rig.event(), rig.event()
+    t0 = time.time()
+    e0.record(rig.cur)
+    for k in range(steps):
+        it = iter(ev[k])
+        next(it).record(rig.cur)
+        step_fn(lambda: next(it).record(rig.cur))
+    e1.record(rig.cur)
+    rig.barrier()
+    rig.windows.append((t0, time.time()))
+    stage_ms = [sum(ev[k][i].elapsed_time(ev[k][i + 1]) for k in range(steps)) / steps for i in range(nmarks)]
+    return e0.elapsed_time(e1), stage_ms
+
+
+def run_decode(args):
+    import ctypes as C
+
+    from vc2_conformance_b200 import capi
+    from vc2_conformance_b200.device import PAD, BatchCodec, SequenceDecoder, _ptr
+
+    rig = Rig(args)
+    torch, dev, world, rank, cur = rig.torch, rig.dev, rig.world, rig.rank, rig.cur
     w = make_workload(args.workload, args.pictures)
     p = w["p"]
     NP = w["pictures"]
@@ -420,17 +525,9 @@ def run_ours(args):
     gen = 8
     for i0 in range(0, NP, gen):
         n = min(gen, NP - i0)
-        pics = synth_pictures(w, rank * NP + i0, n)
-        streams += codec.encode_pictures(pics, w["picture_bytes"])
+        streams += codec.encode_pictures(synth_pictures(w, rank, i0, n), w["picture_bytes"])
     host, offs = codec.pack_host_streams(streams)
     stream_bytes = int(offs[NP])
-    cur = torch.cuda.current_stream()
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     # resident copy of the compressed sequence
     codec._reserve_data(host.numel())
@@ -438,63 +535,55 @@ def run_ours(args):
     codec.pic_offset[: NP + 1].copy_(offs)
     torch.cuda.synchronize()
 
-    # correctness gate of the timed path: decode once, compare with the source of a lossless
-    # re-encode?  (parity itself is the job of tests/; here: status words only)
+    # gate of the timed path: status words and consumed bytes of every picture (values are compared with the
+    # oracle's decode of sample pictures in the cpu_baseline leg below)
     codec.decode_device(codec.data, codec.pic_offset, NP)
     st = codec.status_host(NP)
     assert (st[:, 0] == 0).all(), "decode status not OK"
     assert (st[:, 2] == np.diff(offs.numpy())).all(), "consumed bytes mismatch"
 
-    try:
-        uuid = torch.cuda.get_device_properties(local_rank).uuid
-    except Exception:
-        uuid = None
-    sampler = ClockSampler(local_rank, uuid)
-    sampler.start()
+    rig.sampler.start()
+    L = codec.lib
+    sp = codec._stream_ptr(None)
 
-    # ---- device-resident timed region --------------------------------------------------------
-    for _ in range(args.warmup):
-        codec.decode_device(codec.data, codec.pic_offset, NP)
-    barrier()
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-    e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches0 = codec.launches
-    t_wall0 = time.time()
-    e_start.record(cur)
-    for k in range(args.steps):
-        ev[k][0].record(cur)
-        # stage 1: slice index + unpack (+ dc prediction for LD)
-        import ctypes as C
-
-        from vc2_conformance_b200 import capi
-        from vc2_conformance_b200.device import _ptr
-
-        L = codec.lib
-        sp = codec._stream_ptr(None)
+    def stage_unpack(first, n):
+        d_off = codec.pic_offset[first:]
+        so = codec.slice_offset[first * codec.g.num_slices:]
+        status = codec.status[4 * first:]
         if not p.is_ld:
             capi.check("vc2b_hq_slice_offsets",
-                       L.vc2b_hq_slice_offsets(C.byref(p), _ptr(codec.data), _ptr(codec.pic_offset), NP,
-                                               _ptr(codec.slice_offset), _ptr(codec.status), sp))
+                       L.vc2b_hq_slice_offsets(C.byref(p), _ptr(codec.data), _ptr(d_off), n, _ptr(so), _ptr(status), sp))
         capi.check("vc2b_unpack",
-                   L.vc2b_unpack(C.byref(p), _ptr(codec.data), _ptr(codec.pic_offset), NP,
-                                 _ptr(codec.slice_offset), _ptr(codec.coeffs), _ptr(codec.qindex),
-                                 _ptr(codec.status), sp))
-        ev[k][1].record(cur)
-        codec.idwt_device(NP)
-        ev[k][2].record(cur)
-    e_end.record(cur)
-    barrier()
-    t_wall1 = time.time()
+                   L.vc2b_unpack(C.byref(p), _ptr(codec.data), _ptr(d_off), n, _ptr(so),
+                                 _ptr(codec.coeffs[first * codec.g.picture_coeffs:]),
+                                 _ptr(codec.qindex[first * codec.g.num_slices:]), _ptr(status), sp))
+
+    def make_step(first, n):
+        def step(mark):
+            stage_unpack(first, n)          # stage 1: slice index + unpack (+ dc prediction for LD)
+            mark()
+            codec.idwt_device(n, None, first)  # stage 2: IDWT + crop + clip + offset
+            mark()
+        return step
+
+    # ---- device-resident timed region --------------------------------------------------------
+    launches0 = codec.launches
+    ms_total, (ms_unpack, ms_idwt) = timed(rig, args.steps, args.warmup, make_step(0, NP), 2)
     launches = codec.launches - launches0
-    ms_total = e_start.elapsed_time(e_end)
-    ms_unpack = sum(ev[k][0].elapsed_time(ev[k][1]) for k in range(args.steps)) / args.steps
-    ms_idwt = sum(ev[k][1].elapsed_time(ev[k][2]) for k in range(args.steps)) / args.steps
-    t_ms = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms_max = float(t_ms.item())
+    ms_max = rig.max_ms(ms_total)
     value = world * NP * args.steps / (ms_max / 1000.0)
-    clock_windows = [(t_wall0, t_wall1)]
+
+    # the two kinds of picture on their own (each a contiguous run of the sequence): what the content costs
+    by_content = {}
+    n_noise = (NP + 1) // 2
+    for kind, first, n in (("noise", 0, n_noise), ("ramp", n_noise, NP - n_noise)):
+        if n < 1:
+            continue
+        k_steps = max(3, args.steps // 4)
+        ms_k, (ms_u, ms_i) = timed(rig, k_steps, 1, make_step(first, n), 2)
+        by_content[kind] = {"pictures": n, "pictures_per_s": n * k_steps / (ms_k / 1000.0),
+                            "unpack_us_per_picture": 1000.0 * ms_u / n, "idwt_us_per_picture": 1000.0 * ms_i / n}
+    codec.decode_device(codec.data, codec.pic_offset, NP)  # leave every picture decoded for the checks below
 
     # ---- end-to-end timed region (host buffers) ----------------------------------------------
     e2e = None
@@ -504,39 +593,32 @@ def run_ours(args):
         seq = SequenceDecoder(p, chunk=chunk, nstreams=3, max_chunk_bytes=max_chunk, device=dev)
         chunks = seq.plan(host, offs.numpy())
         out_host = torch.empty((NP, S), dtype=torch.uint16).pin_memory()
-        for _ in range(max(1, args.warmup)):
+
+        def e2e_step(mark):
             seq.fork_from(cur)
             seq.decode(chunks, out_host)
             seq.join_to(cur)
-        barrier()
-        # the e2e path must produce exactly what the resident path produced
-        ref_last = codec.pictures[(NP - 1) * S: NP * S].cpu()
-        assert torch.equal(out_host[NP - 1].view(torch.int16), ref_last.view(torch.int16)), "e2e output mismatch"
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            mark()
+
         l0 = seq.launches
-        t_e2e0 = time.time()
-        s0.record(cur)
-        for _ in range(args.steps):
-            seq.fork_from(cur)
-            seq.decode(chunks, out_host)
-            seq.join_to(cur)
-        s1.record(cur)
-        barrier()
-        clock_windows.append((t_e2e0, time.time()))
-        e2e_ms = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+        e2e_ms, _ = timed(rig, args.steps, max(1, args.warmup), e2e_step, 1)
+        e2e_launches = (seq.launches - l0) * args.steps // (args.steps + max(1, args.warmup))
+        # the e2e path must produce exactly what the resident path produced, for every picture
+        resident = codec.pictures[: NP * S].view(NP, S).view(torch.int16)
+        same = torch.equal(out_host.view(torch.int16), resident.cpu())
+        assert same, "e2e output differs from the resident path"
         e2e = {
-            "value": world * NP * args.steps / (float(e2e_ms.item()) / 1000.0),
+            "value": world * NP * args.steps / (rig.max_ms(e2e_ms) / 1000.0),
             "unit": "pictures/s",
             "h2d_bytes_per_step": int(stream_bytes + 8 * (NP + len(chunks))),
             "d2h_bytes_per_step": int(2 * S * NP),
-            "gpu_launches": seq.launches - l0,
+            "gpu_launches": e2e_launches,
             "pipeline": "%d-picture chunks over 3 CUDA streams" % chunk,
-            "numa_bound_cpus": numa_cpus,
+            "numa_bound_cpus": rig.numa_cpus,
+            "checked": "all %d pictures equal to the resident path" % NP,
         }
-    sampler.stop()
-    clocks = sampler.summary(clock_windows)
+    rig.sampler.stop()
+    clocks = rig.sampler.summary(rig.windows)
 
     # ---- roofline of the stages (algorithmic bytes) -----------------------------
     peak, peak_src = measured_peak()
@@ -548,12 +630,10 @@ def run_ours(args):
     stages = {
         "unpack": {"ms_per_step": ms_unpack, "achieved": unpack_gbs, "frac": unpack_gbs / peak,
                    "algorithmic_bytes_per_picture": unpack_bytes // NP,
-                   "kernels": "hq_walk_kernel + unpack_lanes_kernel<HQ>" if not p.is_ld
-                   else "unpack_lanes_kernel<LD> + dc_prediction_kernel"},
+                   "kernels": "hq_walk_kernel + unpack kernel" if not p.is_ld else "LD unpack kernel + dc_prediction_kernel"},
         "idwt": {"ms_per_step": ms_idwt, "achieved": idwt_gbs, "frac": idwt_gbs / peak,
                  "algorithmic_bytes_per_picture": idwt_bytes // NP,
-                 "kernels": "idwt_stream8_kernel x %d levels (last fused with crop+clip+offset)"
-                            % (p.dwt_depth + p.dwt_depth_ho)},
+                 "kernels": "%d transform levels (last fused with crop+clip+offset)" % (p.dwt_depth + p.dwt_depth_ho)},
     }
     dom = "unpack" if ms_unpack >= ms_idwt else "idwt"
     traffic, traffic_src = None, None
@@ -564,18 +644,28 @@ def run_ours(args):
                 "frac": stages[dom]["frac"], "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_bytes": stages[dom]["algorithmic_bytes_per_picture"] * NP, "peak_source": peak_src}
 
-    # ---- CPU baseline (rank 0, N=1 only) -------------------------------------------------------
-    cpu = None
+    # ---- CPU baseline (rank 0, N=1 only): the oracle also checks the GPU's pictures ---------------
+    cpu, cpu_ref = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sample = streams[:4]
-        rate, cores, npics, secs = cpu_decode_rate(w, sample, budget_s=12.0)
+        idx = sorted(set([0, 1, NP - 2, NP - 1]) & set(range(NP)))  # noise and ramp pictures
+        gpu_pictures = {i: codec.picture_planes(i) for i in idx}
+        checked = []
+
+        def check(k, planes):
+            for c in range(3):
+                assert (planes[c] == gpu_pictures[idx[k]][c]).all(), "GPU picture %d differs from the oracle" % idx[k]
+            checked.append(idx[k])
+
+        rate, cores, npics, secs = cpu_rate(w, "decode", [streams[i] for i in idx], 12.0, check)
         cpu = {"value": rate, "unit": "pictures/s", "cores": cores, "kind": "port",
-               "sample": "%d full-size pictures (4 distinct) decoded by the C oracle on %d threads in %.1f s"
-                         % (npics, cores, secs)}
+               "sample": "%d full-size pictures (%d distinct) decoded by the C oracle on %d threads in %.1f s"
+                         % (npics, len(idx), cores, secs),
+               "checked": "GPU pictures %s bit-exact against the oracle" % sorted(checked)}
+        cpu_ref = python_reference_baseline(args, "decode")
 
     if rank == 0:
         line = {
-            "metric": "decoded pictures/s",
+            "metric": metric_name("decode"),
             "value": value,
             "unit": "pictures/s",
             "n_gpus": world,
@@ -587,24 +677,167 @@ def run_ours(args):
             "vs_baseline": None,
             "dtype": "int32",
             "data": "synthetic",
-            "config": {"workload": w["name"], "pictures_per_step_per_gpu": NP,
+            "config": {"workload": w["name"], "mode": "decode", "pictures_per_step_per_gpu": NP,
                        "bits_per_sample": w["bits_per_sample"], "stream_bytes_per_picture": stream_bytes // NP,
                        "slice_size_scaler": int(p.slice_size_scaler),
-                       "pictures": "even seeds white noise (picture_generators.py:600 recipe), odd seeds integer ramps",
+                       "pictures": "first half white noise (picture_generators.py:600 recipe), second half integer ramps",
                        "l2": "inputs larger than L2 (%.0f MB of streams, %.0f MB of coefficients per step)"
                              % (stream_bytes / 1e6, 4 * padded * NP / 1e6),
                        "idwt_group": args.group},
             "e2e": e2e,
             "roofline": roofline,
             "stages": stages,
+            "stages_by_content": by_content,
             "cpu_baseline": cpu,
+            "cpu_baseline_reference": cpu_ref,
             "gpu_launches": launches,
             "clocks": clocks,
         }
         print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    rig.finish()
+    return 0
+
+
+def run_encode(args):
+    """BASELINE config 5 style: picture_encode (offset removal, padding, DWT) + quantize_to_fit + slice packing."""
+    import ctypes as C
+
+    from vc2_conformance_b200.device import BatchCodec, SequenceEncoder
+
+    rig = Rig(args)
+    torch, dev, world, rank, cur = rig.torch, rig.dev, rig.world, rig.rank, rig.cur
+    w = make_workload(args.workload, args.pictures)
+    p = w["p"]
+    NP = w["pictures"]
+    S = w["samples"]
+    pb = w["picture_bytes"]
+
+    codec = BatchCodec(p, NP, max_stream_bytes=1 << 16, device=dev, group=min(args.group, NP))
+    pics = synth_pictures(w, rank, 0, NP)
+    host_pics = torch.from_numpy(pics.view(np.int16)).view(torch.uint16).pin_memory()
+    codec.upload_pictures(pics)
+    torch.cuda.synchronize()
+    nbytes = int(codec.lib.vc2b_packed_bytes(C.byref(p), pb))
+
+    # gate: the streams decode without error and consume exactly their bytes
+    first_streams = codec.encode_pictures(pics, pb)
+    dec = BatchCodec(p, 1, max_stream_bytes=nbytes + 64, device=dev)
+    for i in sorted(set([0, NP - 1])):
+        dec.decode_streams([first_streams[i]])
+        assert int(dec.status_host(1)[0][2]) == len(first_streams[i]), "decoder did not consume the stream"
+    codec.upload_pictures(pics)
+    out_holder = [None]
+
+    def step(mark):
+        codec.dwt_device(NP)
+        mark()
+        codec.quantize_device(NP, pb)
+        mark()
+        out_holder[0] = codec.pack_device(NP, pb)[0]
+        mark()
+
+    rig.sampler.start()
+    launches0 = codec.launches
+    ms_total, (ms_dwt, ms_fit, ms_pack) = timed(rig, args.steps, args.warmup, step, 3)
+    launches = codec.launches - launches0
+    ms_max = rig.max_ms(ms_total)
+    value = world * NP * args.steps / (ms_max / 1000.0)
+    resident_streams = out_holder[0][:, :nbytes].cpu().numpy()
+
+    e2e = None
+    if not args.no_e2e:
+        chunk = max(1, min(args.chunk, NP // 3 if NP >= 3 else 1))
+        seq = SequenceEncoder(p, pb, chunk=chunk, nstreams=3, device=dev)
+        out_host = torch.empty((NP, seq.stride), dtype=torch.uint8).pin_memory()
+
+        def e2e_step(mark):
+            seq.fork_from(cur)
+            seq.encode(host_pics, out_host)
+            seq.join_to(cur)
+            mark()
+
+        l0 = seq.launches
+        e2e_ms, _ = timed(rig, args.steps, max(1, args.warmup), e2e_step, 1)
+        e2e_launches = (seq.launches - l0) * args.steps // (args.steps + max(1, args.warmup))
+        assert (out_host.numpy()[:, :nbytes] == resident_streams).all(), "e2e streams differ from the resident path"
+        e2e = {
+            "value": world * NP * args.steps / (rig.max_ms(e2e_ms) / 1000.0),
+            "unit": "pictures/s",
+            "h2d_bytes_per_step": int(2 * S * NP),
+            "d2h_bytes_per_step": int(seq.stride * NP),
+            "gpu_launches": e2e_launches,
+            "pipeline": "%d-picture chunks over 3 CUDA streams" % chunk,
+            "numa_bound_cpus": rig.numa_cpus,
+            "checked": "all %d streams equal to the resident path" % NP,
+        }
+    rig.sampler.stop()
+    clocks = rig.sampler.summary(rig.windows)
+
+    peak, peak_src = measured_peak()
+    padded = sum(codec.g.comp_coeffs)
+    dwt_bytes = (2 * S + 4 * padded) * NP              # uint16 pixels in, int32 coefficients out (SURVEY 8d: 6 B/sample)
+    fit_bytes = 4 * padded * NP                        # every coefficient read once (the probes run from shared memory)
+    pack_bytes = (4 * padded + nbytes) * NP            # coefficients in, packed bytes out
+    stages = {}
+    for name, ms, nb_, kern in (("dwt", ms_dwt, dwt_bytes, "DWT levels (first fused with offset removal + padding)"),
+                                ("quantize_to_fit", ms_fit, fit_bytes, "quantize_fit_kernel"),
+                                ("pack", ms_pack, pack_bytes, "pack_slices_kernel")):
+        gbs = nb_ / (ms / 1000.0) / 1e9
+        stages[name] = {"ms_per_step": ms, "achieved": gbs, "frac": gbs / peak,
+                        "algorithmic_bytes_per_picture": nb_ // NP, "kernels": kern}
+    dom = max(stages, key=lambda k: stages[k]["ms_per_step"])
+    roofline = {"bound": "hbm", "stage": dom, "achieved": stages[dom]["achieved"], "peak": peak, "unit": "GB/s",
+                "frac": stages[dom]["frac"], "traffic": None, "traffic_source": None,
+                "algorithmic_bytes": stages[dom]["algorithmic_bytes_per_picture"] * NP, "peak_source": peak_src}
+
+    cpu, cpu_ref = None, None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        idx = sorted(set([0, NP - 1]))
+        checked = []
+
+        def check(k, data):
+            assert data == resident_streams[idx[k]].tobytes(), "GPU stream %d differs from the oracle's" % idx[k]
+            checked.append(idx[k])
+
+        items = [synth_picture(w, rank, i) for i in idx]
+        rate, cores, npics, secs = cpu_rate(w, "encode", items, 12.0, check)
+        cpu = {"value": rate, "unit": "pictures/s", "cores": cores, "kind": "port",
+               "sample": "%d full-size pictures (%d distinct) encoded by the C oracle on %d threads in %.1f s"
+                         % (npics, len(idx), cores, secs),
+               "checked": "GPU streams %s byte-exact against the oracle" % sorted(checked)}
+        cpu_ref = python_reference_baseline(args, "encode")
+
+    if rank == 0:
+        line = {
+            "metric": metric_name("encode"),
+            "value": value,
+            "unit": "pictures/s",
+            "n_gpus": world,
+            "steps": args.steps,
+            "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "int32",
+            "data": "synthetic",
+            "config": {"workload": w["name"], "mode": "encode", "pictures_per_step_per_gpu": NP,
+                       "bits_per_sample": w["bits_per_sample"], "stream_bytes_per_picture": nbytes,
+                       "slice_size_scaler": int(p.slice_size_scaler),
+                       "pictures": "first half white noise (picture_generators.py:600 recipe), second half integer ramps",
+                       "l2": "inputs larger than L2 (%.0f MB of pictures, %.0f MB of coefficients per step)"
+                             % (2 * S * NP / 1e6, 4 * padded * NP / 1e6),
+                       "sharding": "sequence sharded by picture: every rank encodes its own pictures, no collective"},
+            "e2e": e2e,
+            "roofline": roofline,
+            "stages": stages,
+            "cpu_baseline": cpu,
+            "cpu_baseline_reference": cpu_ref,
+            "gpu_launches": launches,
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    rig.finish()
     return 0
 
 
@@ -612,7 +845,7 @@ def main():
     args = parse_args()
     if args.impl == "reference":
         return run_reference(args)
-    return run_ours(args)
+    return run_encode(args) if args.mode == "encode" else run_decode(args)
 
 
 if __name__ == "__main__":

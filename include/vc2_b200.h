@@ -159,6 +159,31 @@ int vc2b_quantize_to_fit(const vc2b_params *p, const int32_t *d_coeffs, int npic
                          int64_t picture_bytes, int minimum_qindex, int32_t *d_qindex,
                          int32_t *d_slice_bits, void *stream);
 
+/* calculate_coeffs_bits (encoder/pictures.py:217) of the Y, C1, C2 (LD: Y, C, 0) blocks of every slice,
+ * quantised (quantize_coeffs :251) at `qindex`, or at d_qindex_in[slice] when that is not NULL -- no
+ * search.  d_qindex_out [npictures*slices] receives the index used, d_slice_bits [npictures*slices*3]
+ * the sizes.  With qindex 0 this is the size pass of make_transform_data_hq_lossless (:528). */
+int vc2b_slice_bits(const vc2b_params *p, const int32_t *d_coeffs, int npictures, int qindex,
+                    const int32_t *d_qindex_in, int32_t *d_qindex_out, int32_t *d_slice_bits, void *stream);
+
+/* quantize_coeffs (encoder/pictures.py:251) for whole pictures: forward_quant (quantization.py:30) of
+ * every coefficient at max(qindex of the slice that holds it - quant_matrix value, 0), the per-slice
+ * index taken from d_qindex [npictures*slices] (or the constant `qindex` when d_qindex is NULL).
+ * d_out has the coefficient layout of d_coeffs (may not alias it). */
+int vc2b_quantize_slices(const vc2b_params *p, const int32_t *d_coeffs, int npictures, const int32_t *d_qindex,
+                         int qindex, int32_t *d_out, void *stream);
+
+/* quantize_to_fit (encoder/pictures.py:295) on explicit lists, the function-level form the reference's
+ * encoder calls per slice: `nsets` (<= 8) coefficient sets stored back to back in d_values
+ * (set s = [set_offsets[s], set_offsets[s+1]), set_offsets is HOST memory), one quantisation matrix value
+ * per coefficient.  d_result[0] = the smallest qindex >= minimum_qindex whose blocks, each padded to
+ * align_bits, total at most target_size bits; d_result[1+s] = calculate_coeffs_bits (:217) of set s at
+ * that index; d_quantised = the quantised values (quantize_coeffs :251).  With target_size = INT64_MAX
+ * and minimum_qindex = q it evaluates quantize_coeffs / calculate_coeffs_bits at q. */
+int vc2b_quantize_to_fit_lists(const int32_t *d_values, const int32_t *d_quant_matrix_values,
+                               const int32_t *set_offsets, int nsets, int64_t target_size, int64_t align_bits,
+                               int minimum_qindex, int32_t *d_result, int32_t *d_quantised, void *stream);
+
 /* Slice packing: the serialisation of hq_slice / ld_slice (bitstream/vc2.py:727-839) with
  * write_sint (bitstream/io.py:575) of the coefficients quantised at d_qindex, producing the
  * same bytes as make_transform_data_hq_lossy/ld_lossy + autofill_and_serialise_stream.
@@ -168,6 +193,20 @@ int64_t vc2b_packed_bytes(const vc2b_params *p, int64_t picture_bytes);
 int vc2b_pack_slices(const vc2b_params *p, const int32_t *d_coeffs, int npictures,
                      int64_t picture_bytes, const int32_t *d_qindex, const int32_t *d_slice_bits,
                      uint8_t *d_out, int64_t out_stride, void *stream);
+
+/* make_transform_data_hq_lossless (encoder/pictures.py:528): every length field is the smallest
+ * multiple of slice_size_scaler bytes that holds its block, so slices have different sizes.
+ * vc2b_hq_lossless_layout turns the block sizes (vc2b_slice_bits at qindex 0) into
+ *   d_slice_offset [npictures*(slices+1)] uint32: byte offset of every slice in its picture's transform
+ *                  data; entry [slices] is the total size
+ *   d_max_length   [npictures] int32: the largest length field at p->slice_size_scaler (the reference
+ *                  picks the scaler from this value at scaler 1: max(1, minimum, (max + 254) // 255)), may be NULL
+ * and vc2b_pack_slices_lossless writes the slices (same bytes as the reference's serialiser). */
+int vc2b_hq_lossless_layout(const vc2b_params *p, const int32_t *d_slice_bits, int npictures,
+                            uint32_t *d_slice_offset, int32_t *d_max_length, void *stream);
+int vc2b_pack_slices_lossless(const vc2b_params *p, const int32_t *d_coeffs, int npictures, const int32_t *d_qindex,
+                              const int32_t *d_slice_bits, const uint32_t *d_slice_offset, uint8_t *d_out,
+                              int64_t out_stride, void *stream);
 
 /* ---- element-wise pseudocode functions ---------------------------------------------- */
 /* inverse_quant / forward_quant (pseudocode/quantization.py:18,30) with per-element index. */

@@ -254,14 +254,75 @@ LIFTING_FILTERS = {
     ),
 }
 
-# Default quantisation matrices (Annex D) are NOT restated: every stream this
-# repo generates carries a custom quantisation matrix.
+# ---------------------------------------------------------------------------
+# Default quantisation matrices (SMPTE ST 2042-1 Annex D).
+#   key = (wavelet_index, wavelet_index_ho, dwt_depth, dwt_depth_ho) -> {level: {orient: value}}
+# Pinning: the Deslauriers-Dubuc (9,7) tables for dwt_depth_ho = 0..4 are quoted verbatim in the
+# reference tree (/root/reference/util/parse_default_quantisation_matrix_table.py:10-55); the
+# dwt_depth_ho = 0 tables of the other six filters are restated from the published standard and
+# are NOT pinned by anything under /root/reference.  Asymmetric tables of the other
+# filters are not restated: such streams need custom_quant_matrix (the reference raises
+# NoQuantisationMatrixAvailable, decoder/picture_syntax.py:331).
+# ---------------------------------------------------------------------------
+
+
+def _sym(ll, rows, depth):
+    """{level: {orient: v}} of a 2-D only transform of `depth` levels."""
+    m = {0: {"LL": ll if depth else 0}}
+    for level in range(1, depth + 1):
+        hl, lh, hh = rows[level - 1]
+        m[level] = {"HL": hl, "LH": lh, "HH": hh}
+    return m
+
+
+def _asym(l, hs, rows, depth, depth_ho):
+    m = {0: {"L": l}}
+    for level in range(1, depth_ho + 1):
+        m[level] = {"H": hs[level - 1]}
+    for level in range(depth_ho + 1, depth_ho + depth + 1):
+        hl, lh, hh = rows[level - depth_ho - 1]
+        m[level] = {"HL": hl, "LH": lh, "HH": hh}
+    return m
+
+
+_SYM_TABLES = {
+    # wavelet: (LL for depth >= 1, per-level (HL, LH, HH)); LL may depend on the depth
+    WaveletFilters.deslauriers_dubuc_9_7: (lambda d: 5, [(3, 3, 0), (4, 4, 1), (5, 5, 2), (6, 6, 3)]),
+    WaveletFilters.le_gall_5_3: (lambda d: 4, [(2, 2, 0), (4, 4, 2), (5, 5, 3), (7, 7, 5)]),
+    WaveletFilters.deslauriers_dubuc_13_7: (lambda d: 5, [(3, 3, 0), (4, 4, 1), (5, 5, 2), (6, 6, 3)]),
+    WaveletFilters.haar_with_shift: (lambda d: 8, [(4, 4, 0), (4, 4, 0), (4, 4, 0), (4, 4, 0)]),
+    WaveletFilters.fidelity: (lambda d: 0, [(4, 4, 8), (8, 8, 12), (13, 13, 17), (17, 17, 21)]),
+    WaveletFilters.daubechies_9_7: (lambda d: 3, [(1, 1, 0), (4, 4, 2), (6, 6, 5), (9, 9, 7)]),
+}
+
 QUANTISATION_MATRICES = {}
+for _w, (_ll, _rows) in _SYM_TABLES.items():
+    for _d in range(0, 5):
+        QUANTISATION_MATRICES[(_w, _w, _d, 0)] = _sym(_ll(_d), _rows, _d)
+# Haar without shift: every level adds 4 from the top down (Table D.4)
+for _d in range(0, 5):
+    QUANTISATION_MATRICES[(WaveletFilters.haar_no_shift, WaveletFilters.haar_no_shift, _d, 0)] = _sym(
+        4 * (_d + 1), [(4 * (_d - _l), 4 * (_d - _l), 4 * (_d - _l - 1)) for _l in range(_d)], _d)
+# Deslauriers-Dubuc (9,7) with horizontal-only levels (quoted in the reference's util script)
+_DD = WaveletFilters.deslauriers_dubuc_9_7
+_DD_HO = {
+    1: ([0], [(3, 3, 0), (4, 4, 1), (5, 5, 2), (6, 6, 3)], 4),
+    2: ([0, 3], [(5, 5, 3), (6, 6, 4), (7, 7, 5)], 3),
+    3: ([0, 3, 5], [(8, 8, 5), (9, 9, 6)], 2),
+    4: ([0, 3, 5, 8], [(10, 10, 8)], 1),
+}
+for _dho, (_hs, _rows, _maxd) in _DD_HO.items():
+    for _d in range(0, _maxd + 1):
+        QUANTISATION_MATRICES[(_DD, _DD, _d, _dho)] = _asym(3, _hs, _rows, _d, _dho)
 
 # ---------------------------------------------------------------------------
-# Header-level tables: import-only placeholders (never used on the picture
-# path).
+# Header-level tables (SMPTE ST 2042-1 clause 11 / Annex C), restated from the published standard.
+# They are consulted by the reference's sequence-header code (set_source_defaults,
+# pseudocode/video_parameters.py:133; encoder/sequence_header.py) -- never by the picture path --
+# and are NOT pinned by anything under /root/reference.
 # ---------------------------------------------------------------------------
+from fractions import Fraction  # noqa: E402
+
 ProfileParameters = namedtuple("ProfileParameters", "allowed_parse_codes")
 PROFILES = {
     Profiles.low_delay: ProfileParameters(
@@ -294,15 +355,82 @@ BaseVideoFormatParameters = namedtuple(
     "top_field_first,frame_rate_index,pixel_aspect_ratio_index,clean_width,"
     "clean_height,left_offset,top_offset,signal_range_index,color_spec_index",
 )
-BASE_VIDEO_FORMAT_PARAMETERS = {}
-PRESET_FRAME_RATES = {}
-PRESET_PIXEL_ASPECT_RATIOS = {}
+_C = ColorDifferenceSamplingFormats
+_P, _I = SourceSamplingModes.progressive, SourceSamplingModes.interlaced
+# index: (width, height, chroma format, sampling, top field first, frame rate, pixel aspect ratio,
+#         clean width, clean height, left, top, signal range, colour spec)   -- Annex C, Table C.1
+_BVF = {
+    0: (640, 480, _C.color_4_2_0, _P, False, 1, 1, 640, 480, 0, 0, 1, 0),
+    1: (176, 120, _C.color_4_2_0, _P, False, 9, 2, 176, 120, 0, 0, 1, 1),
+    2: (176, 144, _C.color_4_2_0, _P, True, 10, 3, 176, 144, 0, 0, 1, 2),
+    3: (352, 240, _C.color_4_2_0, _P, False, 9, 2, 352, 240, 0, 0, 1, 1),
+    4: (352, 288, _C.color_4_2_0, _P, True, 10, 3, 352, 288, 0, 0, 1, 2),
+    5: (704, 480, _C.color_4_2_0, _P, False, 9, 2, 704, 480, 0, 0, 1, 1),
+    6: (704, 576, _C.color_4_2_0, _P, True, 10, 3, 704, 576, 0, 0, 1, 2),
+    7: (720, 480, _C.color_4_2_2, _I, False, 4, 2, 704, 480, 8, 0, 3, 1),
+    8: (720, 576, _C.color_4_2_2, _I, True, 3, 3, 704, 576, 8, 0, 3, 2),
+    9: (1280, 720, _C.color_4_2_2, _P, True, 7, 1, 1280, 720, 0, 0, 3, 3),
+    10: (1280, 720, _C.color_4_2_2, _P, True, 6, 1, 1280, 720, 0, 0, 3, 3),
+    11: (1920, 1080, _C.color_4_2_2, _I, True, 4, 1, 1920, 1080, 0, 0, 3, 3),
+    12: (1920, 1080, _C.color_4_2_2, _I, True, 3, 1, 1920, 1080, 0, 0, 3, 3),
+    13: (1920, 1080, _C.color_4_2_2, _P, True, 7, 1, 1920, 1080, 0, 0, 3, 3),
+    14: (1920, 1080, _C.color_4_2_2, _P, True, 6, 1, 1920, 1080, 0, 0, 3, 3),
+    15: (2048, 1080, _C.color_4_4_4, _P, True, 2, 1, 2048, 1080, 0, 0, 4, 4),
+    16: (4096, 2160, _C.color_4_4_4, _P, True, 2, 1, 4096, 2160, 0, 0, 4, 4),
+    17: (3840, 2160, _C.color_4_2_2, _P, True, 7, 1, 3840, 2160, 0, 0, 3, 5),
+    18: (3840, 2160, _C.color_4_2_2, _P, True, 6, 1, 3840, 2160, 0, 0, 3, 5),
+    19: (7680, 4320, _C.color_4_2_2, _P, True, 7, 1, 7680, 4320, 0, 0, 3, 5),
+    20: (7680, 4320, _C.color_4_2_2, _P, True, 6, 1, 7680, 4320, 0, 0, 3, 5),
+    21: (1920, 1080, _C.color_4_2_2, _P, True, 1, 1, 1920, 1080, 0, 0, 3, 3),
+    22: (720, 486, _C.color_4_2_2, _I, False, 4, 2, 720, 486, 0, 0, 3, 3),
+}
+BASE_VIDEO_FORMAT_PARAMETERS = {
+    BaseVideoFormats(i): BaseVideoFormatParameters(*row) for i, row in _BVF.items()
+}
+PRESET_FRAME_RATES = {
+    PresetFrameRates(i): f
+    for i, f in {
+        1: Fraction(24000, 1001), 2: Fraction(24, 1), 3: Fraction(25, 1), 4: Fraction(30000, 1001),
+        5: Fraction(30, 1), 6: Fraction(50, 1), 7: Fraction(60000, 1001), 8: Fraction(60, 1),
+        9: Fraction(15000, 1001), 10: Fraction(25, 2), 11: Fraction(48, 1), 12: Fraction(48000, 1001),
+        13: Fraction(96, 1), 14: Fraction(100, 1), 15: Fraction(120000, 1001), 16: Fraction(120, 1),
+    }.items()
+}
+PRESET_PIXEL_ASPECT_RATIOS = {
+    PresetPixelAspectRatios(i): f
+    for i, f in {1: Fraction(1, 1), 2: Fraction(10, 11), 3: Fraction(12, 11), 4: Fraction(40, 33),
+                 5: Fraction(16, 11), 6: Fraction(4, 3)}.items()
+}
 SignalRangeParameters = namedtuple(
     "SignalRangeParameters",
     "luma_offset,luma_excursion,color_diff_offset,color_diff_excursion",
 )
-PRESET_SIGNAL_RANGES = {}
-PRESET_COLOR_SPECS = {}
+PRESET_SIGNAL_RANGES = {
+    PresetSignalRanges(i): SignalRangeParameters(*row)
+    for i, row in {
+        1: (0, 255, 128, 255), 2: (16, 219, 128, 224), 3: (64, 876, 512, 896), 4: (256, 3504, 2048, 3584),
+        5: (0, 1023, 512, 1023), 6: (0, 4095, 2048, 4095), 7: (4096, 56064, 32768, 57344),
+        8: (0, 65535, 32768, 65535),
+    }.items()
+}
+ColorSpecificiation = namedtuple(
+    "ColorSpecificiation", "color_primaries_index,color_matrix_index,transfer_function_index"
+)
+_CP, _CM, _TF = PresetColorPrimaries, PresetColorMatrices, PresetTransferFunctions
+PRESET_COLOR_SPECS = {
+    PresetColorSpecs(i): ColorSpecificiation(*row)
+    for i, row in {
+        0: (_CP.hdtv, _CM.hdtv, _TF.tv_gamma),
+        1: (_CP.sdtv_525, _CM.sdtv, _TF.tv_gamma),
+        2: (_CP.sdtv_625, _CM.sdtv, _TF.tv_gamma),
+        3: (_CP.hdtv, _CM.hdtv, _TF.tv_gamma),
+        4: (_CP.d_cinema, _CM.reversible, _TF.d_cinema),
+        5: (_CP.uhdtv, _CM.uhdtv, _TF.tv_gamma),
+        6: (_CP.uhdtv, _CM.uhdtv, _TF.perceptual_quantizer),
+        7: (_CP.uhdtv, _CM.uhdtv, _TF.hybrid_log_gamma),
+    }.items()
+}
+# colour science tables (color_conversion.py) are out of scope: import-only placeholders
 PRESET_COLOR_PRIMARIES = {}
 PRESET_COLOR_MATRICES = {}
 PRESET_TRANSFER_FUNCTIONS = {}

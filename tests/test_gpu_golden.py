@@ -126,11 +126,13 @@ def test_encode_golden_pictures(name):
     codec = BatchCodec(p, 2)
     arg = int(z[name + ".arg"][0])
     lossless = "lossless" in name
-    # lossless HQ = fixed qindex 0 with minimal lengths: give the encoder ample room instead
-    picture_bytes = arg if not lossless else None
     if lossless:
-        pytest.skip("lossless packing (minimal length fields) is exercised in test_gpu_roundtrip")
-    out = codec.encode_pictures(np.stack([pics, pics]), picture_bytes)
+        # make_transform_data_hq_lossless (encoder/pictures.py:528): qindex 0, minimal length fields, the
+        # smallest slice_size_scaler that holds them -- the golden parameters carry the reference's choice
+        scaler, out = codec.encode_pictures_lossless(np.stack([pics, pics]))
+        assert scaler == p.slice_size_scaler
+    else:
+        out = codec.encode_pictures(np.stack([pics, pics]), arg)
     coeffs = codec.coeff_components(1)
     if not p.is_ld:  # (LD: dc prediction has been applied in place)
         for c in range(3):

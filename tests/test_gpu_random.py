@@ -166,6 +166,11 @@ FULL_CASES = [
     ("cfg4_1080p_fidelity_daub_444", dict(luma_width=1920, luma_height=1080, luma_depth=12, wavelet_index=5,
                                           wavelet_index_ho=6, dwt_depth=2, dwt_depth_ho=3, slices_x=60,
                                           slices_y=270, slice_size_scaler=8)),
+    # BASELINE config 5 (the encoder path): 7680x4320 12-bit 4:4:4, 240x270 slices, both filters SURVEY 8(d) names
+    ("cfg5_8k_dd97_d4_444", dict(luma_width=7680, luma_height=4320, luma_depth=12, wavelet_index=0, dwt_depth=4,
+                                 slices_x=240, slices_y=270, slice_size_scaler=16)),
+    ("cfg5_8k_legall_d3_444", dict(luma_width=7680, luma_height=4320, luma_depth=12, wavelet_index=1, dwt_depth=3,
+                                   slices_x=240, slices_y=270, slice_size_scaler=16)),
 ]
 
 
@@ -202,6 +207,42 @@ def test_full_size_roundtrip_and_oracle(name, kw):
         assert (planes[c] == dec[c]).all(), (name, c)
     enc = codec.encode_pictures(flat[0:1], pb)
     assert enc[0] == data
+    # the encoder stages against the oracle: picture_encode coefficients and the per-slice qindex
+    got_coeffs = codec.coeff_components(0)
+    for c in range(3):
+        assert (got_coeffs[c] == coeffs[c]).all(), (name, "picture_encode", c)
+    assert (codec.qindex[:ns].cpu().numpy() == np.asarray(q)).all(), (name, "qindex")
+    # forward_quant of the whole picture at the chosen indices (quantize_coeffs, encoder/pictures.py:251):
+    # inverse-quantising it must give what the decoder unpacked from the stream
+    quantised = codec.quantized_host(1)[0]
+    codec.unpack_streams([data])
+    unpacked = np.concatenate(codec.coeff_components(0))
+    nz = quantised != 0
+    assert ((unpacked != 0) == nz).all(), (name, "quantised zero pattern")
+    assert (np.sign(unpacked) == np.sign(quantised)).all(), (name, "quantised signs")
+
+
+@pytest.mark.parametrize("name,kw", [FULL_CASES[1], FULL_CASES[2]])
+def test_full_size_lossless_encoder(name, kw):
+    """make_transform_data_hq_lossless at full size: minimal length fields, slices of different sizes,
+    packed on the device; decoding gives back the pictures and the oracle agrees on the bytes."""
+    import oracle as O
+    from vc2_conformance_b200.device import BatchCodec
+    from vc2_conformance_b200.params import copy_params
+
+    p = _mk(**kw)
+    S = p.luma_width * p.luma_height + 2 * p.color_diff_width * p.color_diff_height
+    codec = BatchCodec(p, 2, max_stream_bytes=4 * S)
+    pics = [synth.noise_picture(p, 7), synth.ramp_picture(p, 8)]
+    flat = np.stack([synth.flat_picture(pl) for pl in pics])
+    scaler, streams = codec.encode_pictures_lossless(flat)
+    ps = copy_params(p, slice_size_scaler=scaler)
+    dec = BatchCodec(ps, 2, max_stream_bytes=sum(len(s) for s in streams) + 64)
+    out = dec.decode_streams(streams).cpu().numpy()
+    assert (out == flat).all()
+    # the oracle's fixed-qindex-0 serialisation at the same scaler writes the same bytes
+    po = synth.oracle_params(ps)
+    assert O.encode_hq_fixed(po, O.encode_picture(po, pics[1]), 0) == streams[1]
 
 
 def test_full_size_ld_field():

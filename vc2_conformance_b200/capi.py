@@ -119,6 +119,11 @@ SIGNATURES = {
     "vc2b_dwt": (_i, [_PP, _vp, _i, _vp, _vp, _i64, _vp]),
     "vc2b_dwt_raw": (_i, [_PP, _i, _vp, _vp, _vp, _i64, _vp]),
     "vc2b_quantize_to_fit": (_i, [_PP, _vp, _i, _i64, _i, _vp, _vp, _vp]),
+    "vc2b_slice_bits": (_i, [_PP, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "vc2b_quantize_slices": (_i, [_PP, _vp, _i, _vp, _i, _vp, _vp]),
+    "vc2b_quantize_to_fit_lists": (_i, [_vp, _vp, _vp, _i, _i64, _i64, _i, _vp, _vp, _vp]),
+    "vc2b_hq_lossless_layout": (_i, [_PP, _vp, _i, _vp, _vp, _vp]),
+    "vc2b_pack_slices_lossless": (_i, [_PP, _vp, _i, _vp, _vp, _vp, _vp, _i64, _vp]),
     "vc2b_packed_bytes": (_i64, [_PP, _i64]),
     "vc2b_pack_slices": (_i, [_PP, _vp, _i, _i64, _vp, _vp, _vp, _i64, _vp]),
     "vc2b_inverse_quant": (_i, [_vp, _vp, _vp, _i64, _vp]),

@@ -507,7 +507,7 @@ static int launch_fused2(LevelArgs A3, LevelArgs A4, int npic, cudaStream_t s)
     dim3 grid(maxtiles, A4.ncomp, npic);
     using C = Strip8Cfg<FV, FH, 64>;
     const size_t smem = (3 * (kFusedLook + C::EMAX) * 4 * 32 + kRingRows * kRingRowVecs) * sizeof(WideVec);
-    static const cudaError_t attr = cudaFuncSetAttribute(idwt_fused2_kernel<FV, FH>,
+    const cudaError_t attr = cudaFuncSetAttribute(idwt_fused2_kernel<FV, FH>,
                                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (attr != cudaSuccess) return (int)attr;
     idwt_fused2_kernel<FV, FH><<<grid, kFusedThreads, smem, s>>>(A3, A4);

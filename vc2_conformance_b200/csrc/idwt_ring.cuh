@@ -285,7 +285,7 @@ static int launch_ring_steps(LevelArgs A, int npic, cudaStream_t s)
         A.tiles_y[c] = (A.h[c] + C::RSP - 1) / C::RSP;
         maxtiles = max(maxtiles, A.tiles_x[c] * A.tiles_y[c]);
     }
-    static const cudaError_t attr = cudaFuncSetAttribute(idwt_ring_kernel<FV, FH, STEPS>,
+    const cudaError_t attr = cudaFuncSetAttribute(idwt_ring_kernel<FV, FH, STEPS>,
                                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes);
     if (attr != cudaSuccess) return (int)attr;
     dim3 grid(maxtiles, A.ncomp, npic);

@@ -9,9 +9,12 @@
 // video_depth (pseudocode/video_parameters.py:177-206) and the bit reader they use (decoder/io.py:
 // 187-243 read_bit / read_bool / read_nbits / read_uint / byte_align).
 //
-// This is an INDEXER, not a validator: it performs none of the reference's conformance checks, and the
-// tables of the un-vendored vc2_data_tables package (base video formats, default quantisation
-// matrices) are not restated -- a stream that relies on them gets a flag instead of a guess.
+// This is an INDEXER, not a validator: it performs none of the reference's conformance checks.  The tables
+// of the un-vendored vc2_data_tables package that the picture path depends on -- base video formats
+// (frame size, colour difference format, signal range: SMPTE ST 2042-1 Annex C / Table 11.x) and the
+// default quantisation matrices (Annex D) -- are restated from the standard below; a stream that needs an
+// entry this file does not carry gets a flag instead of a guess.  Header fields are untrusted input: every
+// value that sizes or positions a read is range-checked before it is used.
 #include <string.h>
 
 #include "common.cuh"
@@ -68,12 +71,91 @@ struct SeqState {
 bool preset_excursions(uint64_t index, int64_t *luma, int64_t *chroma)
 {
     switch (index) {
-    case 1: *luma = 255; *chroma = 255; return true;    // 8-bit full range
-    case 2: *luma = 219; *chroma = 224; return true;    // 8-bit video
-    case 3: *luma = 876; *chroma = 896; return true;    // 10-bit video
-    case 4: *luma = 3504; *chroma = 3584; return true;  // 12-bit video
+    case 1: *luma = 255; *chroma = 255; return true;      // 8-bit full range
+    case 2: *luma = 219; *chroma = 224; return true;      // 8-bit video
+    case 3: *luma = 876; *chroma = 896; return true;      // 10-bit video
+    case 4: *luma = 3504; *chroma = 3584; return true;    // 12-bit video
+    case 5: *luma = 1023; *chroma = 1023; return true;    // 10-bit full range
+    case 6: *luma = 4095; *chroma = 4095; return true;    // 12-bit full range
+    case 7: *luma = 56064; *chroma = 57344; return true;  // 16-bit video
+    case 8: *luma = 65535; *chroma = 65535; return true;  // 16-bit full range
     default: return false;
     }
+}
+
+// Base video formats (vc2_data_tables.BASE_VIDEO_FORMAT_PARAMETERS; SMPTE ST 2042-1 Annex C): the three
+// columns the picture path needs -- frame size, colour difference format index, signal range preset.
+struct BaseFormat { int32_t width, height, cdf, signal_range; };
+const BaseFormat kBaseFormats[23] = {
+    {640, 480, 2, 1},    // 0  custom format
+    {176, 120, 2, 1},    // 1  QSIF525
+    {176, 144, 2, 1},    // 2  QCIF
+    {352, 240, 2, 1},    // 3  SIF525
+    {352, 288, 2, 1},    // 4  CIF
+    {704, 480, 2, 1},    // 5  4SIF525
+    {704, 576, 2, 1},    // 6  4CIF
+    {720, 480, 1, 3},    // 7  SD480I-60
+    {720, 576, 1, 3},    // 8  SD576I-50
+    {1280, 720, 1, 3},   // 9  HD720P-60
+    {1280, 720, 1, 3},   // 10 HD720P-50
+    {1920, 1080, 1, 3},  // 11 HD1080I-60
+    {1920, 1080, 1, 3},  // 12 HD1080I-50
+    {1920, 1080, 1, 3},  // 13 HD1080P-60
+    {1920, 1080, 1, 3},  // 14 HD1080P-50
+    {2048, 1080, 0, 4},  // 15 DC2K
+    {4096, 2160, 0, 4},  // 16 DC4K
+    {3840, 2160, 1, 3},  // 17 UHDTV 4K-60
+    {3840, 2160, 1, 3},  // 18 UHDTV 4K-50
+    {7680, 4320, 1, 3},  // 19 UHDTV 8K-60
+    {7680, 4320, 1, 3},  // 20 UHDTV 8K-50
+    {1920, 1080, 1, 3},  // 21 HD1080P-24
+    {720, 486, 1, 3},    // 22 SD Pro486
+};
+
+// Default quantisation matrices (vc2_data_tables.QUANTISATION_MATRICES; SMPTE ST 2042-1 Annex D) of the
+// symmetric transforms (wavelet_index == wavelet_index_ho, dwt_depth_ho == 0, dwt_depth <= 4) and of
+// Deslauriers-Dubuc (9,7) with horizontal-only levels (the tables quoted in the reference tree:
+// util/parse_default_quantisation_matrix_table.py:10-55).  Returns false where no table is carried.
+bool default_quant_matrix(vc2b_params *p)
+{
+    const int w = p->wavelet_index, d = p->dwt_depth, dho = p->dwt_depth_ho;
+    if (w != p->wavelet_index_ho || w < 0 || w > 6 || d < 0 || dho < 0) return false;
+    memset(p->quant_matrix, 0, sizeof(p->quant_matrix));
+    if (dho == 0) {
+        if (d > 4) return false;
+        // rows: HL = LH, HH of 2-D level 1..4; LL of depth >= 1
+        static const int ll[7] = {5, 4, 5, 0 /* Haar, no shift: 4 * (depth + 1) */, 8, 0, 3};
+        static const int hl[7][4] = {{3, 4, 5, 6}, {2, 4, 5, 7}, {3, 4, 5, 6}, {0, 0, 0, 0}, {4, 4, 4, 4},
+                                     {4, 8, 13, 17}, {1, 4, 6, 9}};
+        static const int hh[7][4] = {{0, 1, 2, 3}, {0, 2, 3, 5}, {0, 1, 2, 3}, {0, 0, 0, 0}, {0, 0, 0, 0},
+                                     {8, 12, 17, 21}, {0, 2, 5, 7}};
+        if (d == 0) return true;  // a single LL band: 0
+        if (w == 3) {             // Haar without shift: every level adds 4 from the top down
+            p->quant_matrix[0][0] = 4 * (d + 1);
+            for (int l = 1; l <= d; l++) {
+                p->quant_matrix[l][1] = p->quant_matrix[l][2] = 4 * (d - l + 1);
+                p->quant_matrix[l][3] = 4 * (d - l);
+            }
+            return true;
+        }
+        p->quant_matrix[0][0] = ll[w];
+        for (int l = 1; l <= d; l++) {
+            p->quant_matrix[l][1] = p->quant_matrix[l][2] = hl[w][l - 1];
+            p->quant_matrix[l][3] = hh[w][l - 1];
+        }
+        return true;
+    }
+    if (w != 0 || dho > 4 || d > 5 - dho || (dho == 1 && d > 4)) return false;
+    static const int h_levels[4] = {0, 3, 5, 8};
+    static const int hl_ho[5][4] = {{0, 0, 0, 0}, {3, 4, 5, 6}, {5, 6, 7, 0}, {8, 9, 0, 0}, {10, 0, 0, 0}};
+    static const int hh_ho[5][4] = {{0, 0, 0, 0}, {0, 1, 2, 3}, {3, 4, 5, 0}, {5, 6, 0, 0}, {8, 0, 0, 0}};
+    p->quant_matrix[0][0] = 3;
+    for (int l = 1; l <= dho; l++) p->quant_matrix[l][1] = h_levels[l - 1];
+    for (int l = 1; l <= d; l++) {
+        p->quant_matrix[dho + l][1] = p->quant_matrix[dho + l][2] = hl_ho[dho][l - 1];
+        p->quant_matrix[dho + l][3] = hh_ho[dho][l - 1];
+    }
+    return true;
 }
 
 void read_sequence_header(BitReader &r, SeqState &s)
@@ -119,14 +201,29 @@ void read_sequence_header(BitReader &r, SeqState &s)
         }
     }
     s.picture_coding_mode = (int32_t)r.uint();
-    if (s.frame_width < 0 || s.color_diff_format_index < 0 || s.luma_excursion < 0)
-        s.flags |= VC2B_IDX_NEEDS_BASE_FORMAT;  // the base video format supplies what the stream does not override
+    // the base video format supplies what the stream does not override (set_source_defaults,
+    // pseudocode/video_parameters.py:133)
+    if (s.frame_width < 0 || s.color_diff_format_index < 0 || s.luma_excursion < 0) {
+        if (s.base_video_format < 0 || s.base_video_format > 22) {
+            s.flags |= VC2B_IDX_NEEDS_BASE_FORMAT;  // an index the table does not carry
+        } else {
+            const BaseFormat &b = kBaseFormats[s.base_video_format];
+            if (s.frame_width < 0) { s.frame_width = b.width; s.frame_height = b.height; }
+            if (s.color_diff_format_index < 0) s.color_diff_format_index = b.cdf;
+            if (s.luma_excursion < 0) preset_excursions((uint64_t)b.signal_range, &s.luma_excursion, &s.color_diff_excursion);
+        }
+    }
+    // untrusted sizes: anything the picture path cannot represent is flagged, not used
+    if (s.frame_width < 1 || s.frame_height < 1 || s.frame_width > (1 << 20) || s.frame_height > (1 << 20) ||
+        s.color_diff_format_index > 2 || s.luma_excursion < 1 || s.color_diff_excursion < 1 ||
+        s.luma_excursion > 0xffffffffLL || s.color_diff_excursion > 0xffffffffLL)
+        s.flags |= VC2B_IDX_UNSUPPORTED;
 }
 
 // picture_dimensions + video_depth (pseudocode/video_parameters.py:177-206)
 void fill_dimensions(const SeqState &s, vc2b_params *p)
 {
-    if (!s.have || (s.flags & VC2B_IDX_NEEDS_BASE_FORMAT)) return;
+    if (!s.have || (s.flags & (VC2B_IDX_NEEDS_BASE_FORMAT | VC2B_IDX_UNSUPPORTED))) return;
     int64_t lw = s.frame_width, lh = s.frame_height, cw = lw, ch = lh;
     if (s.color_diff_format_index == 1) cw /= 2;                 // 4:2:2
     if (s.color_diff_format_index == 2) { cw /= 2; ch /= 2; }    // 4:2:0
@@ -152,16 +249,32 @@ void read_transform_parameters(BitReader &r, const SeqState &s, int code, vc2b_p
         if (r.boolean()) p->wavelet_index_ho = (int32_t)r.uint();
         if (r.boolean()) p->dwt_depth_ho = (int32_t)r.uint();
     }
-    p->slices_x = (int32_t)r.uint();  // slice_parameters (:175)
-    p->slices_y = (int32_t)r.uint();
+    // slice_parameters (:175).  Untrusted: values that do not fit the fields, or that would make the slice
+    // walk below overflow, mark the unit unsupported (the casts alone would let them go negative)
+    const uint64_t kMaxField = 0x7fffffffull;
+    uint64_t v[4];
+    v[0] = r.uint();
+    v[1] = r.uint();
+    v[2] = r.uint();
+    v[3] = r.uint();
     p->slice_size_scaler = 1;
     p->slice_bytes_denominator = 1;
-    if (ld) {
-        p->slice_bytes_numerator = (int64_t)r.uint();
-        p->slice_bytes_denominator = (int64_t)r.uint();
+    bool bad = v[0] < 1 || v[1] < 1 || v[0] > kMaxField || v[1] > kMaxField || v[0] * v[1] > kMaxField ||
+               (uint64_t)p->wavelet_index > 6 || (uint64_t)p->wavelet_index_ho > 6;
+    if (ld) bad = bad || v[3] < 1 || v[2] > (1ull << 40) || v[3] > (1ull << 40);  // slices * numerator < 2^71 / 2^8
+    else bad = bad || v[2] > (1u << 24) || v[3] < 1 || v[3] > (1u << 24);
+    if (bad) {
+        *flags |= VC2B_IDX_UNSUPPORTED;
     } else {
-        p->slice_prefix_bytes = (int32_t)r.uint();
-        p->slice_size_scaler = (int32_t)r.uint();
+        p->slices_x = (int32_t)v[0];
+        p->slices_y = (int32_t)v[1];
+        if (ld) {
+            p->slice_bytes_numerator = (int64_t)v[2];
+            p->slice_bytes_denominator = (int64_t)v[3];
+        } else {
+            p->slice_prefix_bytes = (int32_t)v[2];
+            p->slice_size_scaler = (int32_t)v[3];
+        }
     }
     if (r.boolean()) {  // quant_matrix (:267), custom
         const int dho = p->dwt_depth_ho, d = p->dwt_depth;
@@ -173,8 +286,10 @@ void read_transform_parameters(BitReader &r, const SeqState &s, int code, vc2b_p
             p->quant_matrix[level][2] = (int32_t)r.uint();  // LH
             p->quant_matrix[level][3] = (int32_t)r.uint();  // HH
         }
-    } else {
-        *flags |= VC2B_IDX_NEEDS_DEFAULT_QUANT_MATRIX;  // vc2_data_tables.QUANTISATION_MATRICES
+    } else if (p->dwt_depth < 0 || p->dwt_depth_ho < 0 || p->dwt_depth_ho + p->dwt_depth + 1 > VC2B_MAX_LEVELS) {
+        *flags |= VC2B_IDX_UNSUPPORTED;
+    } else if (!default_quant_matrix(p)) {
+        *flags |= VC2B_IDX_NEEDS_DEFAULT_QUANT_MATRIX;  // a vc2_data_tables.QUANTISATION_MATRICES entry not carried here
     }
 }
 
@@ -259,22 +374,28 @@ int64_t vc2b_index_stream(const uint8_t *data, int64_t len, vc2b_unit *units, in
             // Without a next_parse_offset the end of a picture is only known by walking its slices.
             if (picture && !(u.flags & (VC2B_IDX_TRUNCATED | VC2B_IDX_UNSUPPORTED)) && u.params.slices_x > 0 &&
                 u.params.slices_y > 0) {
+                // slices_x * slices_y < 2^31, numerator <= 2^40, prefix and scaler <= 2^24 (checked when they
+                // were read): every product below fits 128 / 64 bits and p only ever grows
                 const int64_t ns = (int64_t)u.params.slices_x * u.params.slices_y;
                 int64_t p = u.data_offset;
                 if (u.params.is_ld) {
-                    p += (ns * u.params.slice_bytes_numerator) / (u.params.slice_bytes_denominator > 0
-                                                                      ? u.params.slice_bytes_denominator : 1);
+                    const unsigned __int128 total = ((unsigned __int128)ns * (unsigned __int128)u.params.slice_bytes_numerator) /
+                                                    (unsigned __int128)u.params.slice_bytes_denominator;
+                    p = total > (unsigned __int128)(len - p) ? len : p + (int64_t)total;
                 } else {
                     for (int64_t i = 0; i < ns && p < len; i++) {  // hq_slice (transform_data_syntax.py:212)
-                        p += u.params.slice_prefix_bytes + 1;
+                        p += (int64_t)u.params.slice_prefix_bytes + 1;
                         for (int c = 0; c < 3 && p < len; c++) p += 1 + (int64_t)data[p] * u.params.slice_size_scaler;
                     }
+                    if (p > len) p = len;
                 }
+                if (p <= off || p < u.data_offset) break;  // no progress: nothing says where the next unit starts
                 off = p;
                 continue;
             }
             break;  // nothing says where the next data unit starts
         }
+        if (next < 13 || next > len - off) break;  // a next_parse_offset that does not lead to another header
         off += next;
     }
     return n;

@@ -2,6 +2,9 @@
 //
 // Restates pseudocode/slice_sizes.py:53-92 (subband_width / subband_height) and
 // the subband ordering of decoder/transform_data_syntax.py:176-189,230-243.
+#include <map>
+#include <mutex>
+
 #include "lifting.cuh"
 
 namespace vc2b {
@@ -118,7 +121,7 @@ static PassGain pass_gain(int filter, bool analysis)
     const int lens[5] = {2, 4, 8, 16, 64};
     for (int li = 0; li < 5; li++) {
         const int N = lens[li];
-        static double M[64][64];
+        double M[64][64];  // a local: host threads may call concurrently (ctypes releases the GIL)
         for (int r = 0; r < N; r++)
             for (int c = 0; c < N; c++) M[r][c] = r == c ? 1.0 : 0.0;
         for (int k = 0; k < f.nstages; k++) {
@@ -203,14 +206,29 @@ static double dwt_worst(const vc2b_params *p, double m)
     return worst;
 }
 
+// The bound only depends on the filters and depths; the bisection costs a millisecond or two of host
+// time, which vc2b_unpack would otherwise pay on every call: cache it per transform (mutex: ctypes
+// callers may be on several host threads).
+static std::mutex g_safe_mutex;
+static std::map<uint32_t, long long> g_safe_cache;
+
 long long idwt_max_safe_coeff(const vc2b_params *p)
 {
+    const uint32_t key = ((uint32_t)(p->wavelet_index & 0xff) << 24) | ((uint32_t)(p->wavelet_index_ho & 0xff) << 16) |
+                         ((uint32_t)(p->dwt_depth & 0xff) << 8) | (uint32_t)(p->dwt_depth_ho & 0xff);
+    {
+        std::lock_guard<std::mutex> lock(g_safe_mutex);
+        auto it = g_safe_cache.find(key);
+        if (it != g_safe_cache.end()) return it->second;
+    }
     const double limit = 2147483647.0;
     long long lo = 0, hi = 0x7fffffffLL;  // largest m with idwt_worst(m) <= limit
     while (lo < hi) {
         long long mid = (lo + hi + 1) >> 1;
         if (idwt_worst(p, (double)mid) <= limit) lo = mid; else hi = mid - 1;
     }
+    std::lock_guard<std::mutex> lock(g_safe_mutex);
+    g_safe_cache[key] = lo;
     return lo;
 }
 

@@ -7,6 +7,8 @@
 // quantize_to_fit (encoder/pictures.py:217-347) as driven by make_transform_data_hq_lossy
 // (:617) and make_transform_data_ld_lossy (:724), and the serialisation of hq_slice / ld_slice
 // (bitstream/vc2.py:727-839) with write_sint (bitstream/io.py:557-583).
+#include <string.h>
+
 #include "common.cuh"
 
 namespace vc2b {
@@ -336,6 +338,10 @@ struct FitArgs {
     int max_qm;
     int stage_cap;                // coefficients the per-warp staging area holds (quantize_fit_kernel)
     int use_map;                  // every band fits the 24-bit offsets of FitMap
+    int fixed_qindex;             // >= 0: no search, only the block sizes at this index (vc2b_slice_bits)
+    const int32_t *fixed_per_slice;  // != nullptr: no search, block sizes at the slice's own index
+    const uint32_t *lossless_offset; // packer, make_transform_data_hq_lossless (:528): [npictures * (slices + 1)]
+                                     // byte offset of every slice inside its picture; minimal length fields
 };
 
 __device__ __forceinline__ long long hq_total_length(const DevParams &P, const FitArgs &F, long long n)
@@ -554,7 +560,9 @@ quantize_fit_kernel(DevParams P, FitArgs F, const int32_t *__restrict__ coeffs, 
     // so the reference's linear search (quantize_to_fit :329) equals this bisection.
     int lo = F.minimum_qindex;
     int hi = max(lo, 128 + F.max_qm + 4);  // everything quantises to zero here (int32 envelope)
-    if (target < 0) {
+    if (F.fixed_qindex >= 0 || F.fixed_per_slice) {
+        lo = hi = F.fixed_per_slice ? F.fixed_per_slice[gw] : F.fixed_qindex;  // sizes only, no search
+    } else if (target < 0) {
         lo = hi;  // cannot fit: reported as the saturated index (the reference would not terminate)
     } else {
         // Neighbouring slices of a picture usually need almost the same index: gallop outwards from
@@ -772,12 +780,17 @@ pack_slices_kernel(DevParams P, FitArgs F, const int32_t *__restrict__ coeffs, i
         // length byte and a bounded block of 8*scaler*length bits (make_hq_slice :456)
         const long long scaler = P.slice_size_scaler;
         const long long den = (long long)nslices * scaler;
-        const long long off = (long long)n * (P.slice_prefix_bytes + 4) + scaler * ((n * F.total_coeff_bytes) / den);
-        const long long total_length = hq_total_length(P, F, n);
         const long long align = 8 * scaler;
         const long long ly = (bits_in[3 * gw + 0] + align - 1) / align;
         const long long l1 = (bits_in[3 * gw + 1] + align - 1) / align;
-        const long long l2 = total_length - ly - l1;
+        long long off, l2;
+        if (F.lossless_offset) {  // every length field minimal (make_hq_slice total_length=None, :456)
+            off = F.lossless_offset[(long long)pic * (nslices + 1) + n];
+            l2 = (bits_in[3 * gw + 2] + align - 1) / align;
+        } else {
+            off = (long long)n * (P.slice_prefix_bytes + 4) + scaler * ((n * F.total_coeff_bytes) / den);
+            l2 = hq_total_length(P, F, n) - ly - l1;
+        }
         long long pos = pic_bit0 + 8 * (off + P.slice_prefix_bytes);
         const long long big = 0x7fffffffffffffffLL;
         if (lane == 0) {
@@ -796,6 +809,152 @@ pack_slices_kernel(DevParams P, FitArgs F, const int32_t *__restrict__ coeffs, i
         pack_block<false>(TC, P.nb, pc + P.comp_off[2], nullptr, nc, qtab, out32, pos, pos + align * l2, lane, map_c);
     }
   }  // slices of this warp
+}
+
+// ---------------------------------------------------------------------------
+// whole-picture quantize_coeffs (encoder/pictures.py:251): forward_quant of every coefficient at
+// max(qindex of its slice - quant matrix value, 0); output in the coefficient layout
+// ---------------------------------------------------------------------------
+__global__ void quantize_slices_kernel(DevParams P, const int32_t *__restrict__ coeffs, int npictures,
+                                       const int32_t *__restrict__ qindex, int fixed_qindex, int32_t *__restrict__ out)
+{
+    const int c = blockIdx.y;
+    const int pic = blockIdx.z;
+    const int32_t *src = coeffs + (size_t)pic * P.pic_coeffs + P.comp_off[c];
+    int32_t *dst = out + (size_t)pic * P.pic_coeffs + P.comp_off[c];
+    const int32_t *qi = qindex ? qindex + (size_t)pic * P.slices_x * P.slices_y : nullptr;
+    for (int b = 0; b < P.nb; b++) {
+        const Band B = P.band[c][b];
+        const long long n = (long long)B.w * B.h;
+        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+            const int y = (int)(i / B.w), x = (int)(i - (long long)y * B.w);
+            // the slice whose rectangle holds (x, y): largest s with (w * s) // slices <= x (slice_sizes.py:108)
+            const int sx = (int)((((long long)x + 1) * P.slices_x - 1) / B.w);
+            const int sy = (int)((((long long)y + 1) * P.slices_y - 1) / B.h);
+            const int q = qi ? qi[sy * P.slices_x + sx] : fixed_qindex;
+            const int32_t v = src[B.off + i];
+            const uint32_t m = v < 0 ? (uint32_t)(-(long long)v) : (uint32_t)v;
+            const uint32_t r = forward_quant_mag(m, quant_factor_u64(max(q - B.qm, 0)));
+            dst[B.off + i] = v < 0 ? -(int32_t)r : (int32_t)r;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// make_transform_data_hq_lossless (encoder/pictures.py:528): the slices of a picture follow each other
+// with minimal length fields, so a slice's offset is a prefix sum over the sizes of the slices before it
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+hq_lossless_layout_kernel(DevParams P, const int32_t *__restrict__ bits, int npictures, uint32_t *__restrict__ offset,
+                          int32_t *__restrict__ max_length)
+{
+    __shared__ unsigned long long warp_sum[32];
+    __shared__ unsigned long long carry;
+    __shared__ int smax;
+    const int pic = blockIdx.x;
+    const int nslices = P.slices_x * P.slices_y;
+    const long long align = 8LL * P.slice_size_scaler;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { carry = 0; smax = 0; }
+    __syncthreads();
+    int mymax = 0;
+    for (int n0 = 0; n0 < nslices; n0 += blockDim.x) {
+        const int n = n0 + threadIdx.x;
+        unsigned long long sz = 0;
+        if (n < nslices) {
+            const int32_t *b = bits + 3 * ((size_t)pic * nslices + n);
+            long long len = 0;
+            for (int k = 0; k < 3; k++) {
+                const long long l = (b[k] + align - 1) / align;
+                mymax = max(mymax, (int)min(l, 0x7fffffffLL));
+                len += l;
+            }
+            sz = (unsigned long long)(P.slice_prefix_bytes + 4 + P.slice_size_scaler * len);
+        }
+        unsigned long long pre = sz;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long o = __shfl_up_sync(0xffffffffu, pre, d);
+            if (lane >= d) pre += o;
+        }
+        if (lane == 31) warp_sum[warp] = pre;
+        __syncthreads();
+        unsigned long long base = carry;
+        for (int w = 0; w < warp; w++) base += warp_sum[w];
+        if (n < nslices) offset[(size_t)pic * (nslices + 1) + n] = (uint32_t)(base + pre - sz);
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = base + pre;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) offset[(size_t)pic * (nslices + 1) + nslices] = (uint32_t)carry;
+    atomicMax(&smax, mymax);
+    __syncthreads();
+    if (threadIdx.x == 0 && max_length) max_length[pic] = smax;
+}
+
+// ---------------------------------------------------------------------------
+// quantize_to_fit (encoder/pictures.py:295) on explicit coefficient lists: the function-level drop-in
+// (one CTA; the lists of one slice).  result[0] = qindex, result[1 + s] = calculate_coeffs_bits of set s.
+// ---------------------------------------------------------------------------
+constexpr int kListSets = 8;
+struct ListArgs {
+    int nsets;
+    int set_off[kListSets + 1];
+    long long target, align;
+    int minimum_qindex, max_qindex;
+};
+
+__global__ void __launch_bounds__(256)
+quantize_fit_lists_kernel(ListArgs A, const int32_t *__restrict__ values, const int32_t *__restrict__ qm,
+                          int32_t *__restrict__ result, int32_t *__restrict__ quantised)
+{
+    __shared__ long long s_bits[kListSets];
+    __shared__ int s_last[kListSets];
+    __shared__ int s_done;
+    const int n = A.set_off[A.nsets];
+    for (int q = A.minimum_qindex;; q++) {
+        if (threadIdx.x < kListSets) { s_bits[threadIdx.x] = 0; s_last[threadIdx.x] = -1; }
+        __syncthreads();
+        for (int s = 0; s < A.nsets; s++) {
+            long long sum = 0;
+            int last = -1;
+            for (int i = A.set_off[s] + threadIdx.x; i < A.set_off[s + 1]; i += blockDim.x) {
+                const int32_t v = values[i];
+                const uint32_t m = v < 0 ? (uint32_t)(-(long long)v) : (uint32_t)v;
+                const uint32_t r = forward_quant_mag(m, quant_factor_u64(max(q - qm[i], 0)));
+                sum += sint_length(r);
+                if (r) last = i;
+            }
+            atomicAdd((unsigned long long *)&s_bits[s], (unsigned long long)sum);
+            atomicMax(&s_last[s], last);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            long long total = 0;
+            for (int s = 0; s < A.nsets; s++) {
+                // trailing zeros are free (calculate_coeffs_bits :217)
+                const long long b = s_last[s] < 0 ? 0 : s_bits[s] - (A.set_off[s + 1] - 1 - s_last[s]);
+                s_bits[s] = b;
+                total += ((b + A.align - 1) / A.align) * A.align;
+            }
+            s_done = (total <= A.target || q >= A.max_qindex) ? 1 : 0;
+        }
+        __syncthreads();
+        if (s_done) {
+            if (threadIdx.x == 0) {
+                result[0] = q;
+                for (int s = 0; s < A.nsets; s++) result[1 + s] = (int32_t)s_bits[s];
+            }
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                const int32_t v = values[i];
+                const uint32_t m = v < 0 ? (uint32_t)(-(long long)v) : (uint32_t)v;
+                const uint32_t r = forward_quant_mag(m, quant_factor_u64(max(q - qm[i], 0)));
+                quantised[i] = v < 0 ? -(int32_t)r : (int32_t)r;
+            }
+            return;
+        }
+        __syncthreads();
+    }
 }
 
 static int max_qm(const DevParams &P)
@@ -843,23 +1002,29 @@ int vc2b_clip_offset(int32_t *d_data, int64_t n, int depth, int mode, void *stre
     return 0;
 }
 
-int vc2b_quantize_to_fit(const vc2b_params *p, const int32_t *d_coeffs, int npictures, int64_t picture_bytes,
-                         int minimum_qindex, int32_t *d_qindex, int32_t *d_slice_bits, void *stream)
+// shared by vc2b_quantize_to_fit (search) and vc2b_slice_bits (sizes at a given index)
+static int launch_fit(const vc2b_params *p, const int32_t *d_coeffs, int npictures, int64_t picture_bytes,
+                      int minimum_qindex, int fixed_qindex, const int32_t *d_fixed, int32_t *d_qindex,
+                      int32_t *d_slice_bits, void *stream)
 {
     DevParams P;
     int st = make_dev_params(p, &P);
     if (st) return st;
     if (npictures <= 0) return 0;
     FitArgs F;
+    memset(&F, 0, sizeof(F));
+    const bool search = fixed_qindex < 0 && !d_fixed;
     const long long nslices = (long long)P.slices_x * P.slices_y;
     F.total_coeff_bytes = picture_bytes - 4 * nslices;
-    if (!P.is_ld && F.total_coeff_bytes < 0) return VC2B_E_BAD_PARAMS;  // InsufficientHQPictureBytesError
-    if (!P.is_ld) {
+    if (search && !P.is_ld && F.total_coeff_bytes < 0) return VC2B_E_BAD_PARAMS;  // InsufficientHQPictureBytesError
+    if (search && !P.is_ld) {
         // every length field must fit 8 bits (get_safe_lossy_hq_slice_size_scaler, encoder/pictures.py:586)
         const long long den = nslices * P.slice_size_scaler;
         if ((F.total_coeff_bytes + den - 1) / den > 255) return VC2B_E_BAD_PARAMS;
     }
     F.minimum_qindex = minimum_qindex < 0 ? 0 : minimum_qindex;
+    F.fixed_qindex = search ? -1 : (fixed_qindex < 0 ? 0 : fixed_qindex);
+    F.fixed_per_slice = d_fixed;
     F.max_qm = max_qm(P);
     // staging area: the largest slice (every band rectangle is at most ceil(w / slices_x) x ceil(h / slices_y))
     long long cap = 0;
@@ -873,9 +1038,10 @@ int vc2b_quantize_to_fit(const vc2b_params *p, const int32_t *d_coeffs, int npic
         for (int b = 0; b < P.nb; b++)
             if ((long long)P.band[c][b].w * P.band[c][b].h >= (1 << 24)) F.use_map = 0;
     const size_t smem = kQWarps * slice_stage_bytes(F.stage_cap);
-    {   // static + dynamic shared memory can exceed the 48 KB default for the largest staged slices
-        static const cudaError_t attr = cudaFuncSetAttribute(quantize_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                             (int)(kQWarps * slice_stage_bytes(kStageMax)));
+    {   // static + dynamic shared memory can exceed the 48 KB default for the largest staged slices;
+        // the attribute is per device, so it is set on every call (cheap) rather than once per process
+        const cudaError_t attr = cudaFuncSetAttribute(quantize_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                      (int)(kQWarps * slice_stage_bytes(kStageMax)));
         if (attr != cudaSuccess) return (int)attr;
     }
     const long long warps = npictures * nslices;
@@ -884,6 +1050,73 @@ int vc2b_quantize_to_fit(const vc2b_params *p, const int32_t *d_coeffs, int npic
     if (nblk > 148LL * 16) nblk = 148LL * 16;
     quantize_fit_kernel<<<(unsigned)nblk, kQWarps * 32, smem, (cudaStream_t)stream>>>(
         P, F, d_coeffs, npictures, d_qindex, d_slice_bits);
+    VC2B_CHECK_LAUNCH();
+    return 0;
+}
+
+int vc2b_quantize_to_fit(const vc2b_params *p, const int32_t *d_coeffs, int npictures, int64_t picture_bytes,
+                         int minimum_qindex, int32_t *d_qindex, int32_t *d_slice_bits, void *stream)
+{
+    return launch_fit(p, d_coeffs, npictures, picture_bytes, minimum_qindex, -1, nullptr, d_qindex, d_slice_bits, stream);
+}
+
+int vc2b_slice_bits(const vc2b_params *p, const int32_t *d_coeffs, int npictures, int qindex,
+                    const int32_t *d_qindex_in, int32_t *d_qindex_out, int32_t *d_slice_bits, void *stream)
+{
+    if (!d_slice_bits || !d_qindex_out) return VC2B_E_BAD_PARAMS;
+    return launch_fit(p, d_coeffs, npictures, 0, 0, qindex < 0 ? 0 : qindex, d_qindex_in, d_qindex_out, d_slice_bits,
+                      stream);
+}
+
+int vc2b_quantize_slices(const vc2b_params *p, const int32_t *d_coeffs, int npictures, const int32_t *d_qindex,
+                         int qindex, int32_t *d_out, void *stream)
+{
+    DevParams P;
+    int st = make_dev_params(p, &P);
+    if (st) return st;
+    if (npictures <= 0) return 0;
+    long long biggest = 1;
+    for (int b = 0; b < P.nb; b++) biggest = max(biggest, (long long)P.band[0][b].w * P.band[0][b].h);
+    dim3 grid(grid_for(biggest, 256), 3, npictures);
+    quantize_slices_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P, d_coeffs, npictures, d_qindex, qindex < 0 ? 0 : qindex,
+                                                                   d_out);
+    VC2B_CHECK_LAUNCH();
+    return 0;
+}
+
+int vc2b_hq_lossless_layout(const vc2b_params *p, const int32_t *d_slice_bits, int npictures,
+                            uint32_t *d_slice_offset, int32_t *d_max_length, void *stream)
+{
+    DevParams P;
+    int st = make_dev_params(p, &P);
+    if (st) return st;
+    if (P.is_ld) return VC2B_E_BAD_PARAMS;
+    if (npictures <= 0) return 0;
+    hq_lossless_layout_kernel<<<npictures, 1024, 0, (cudaStream_t)stream>>>(P, d_slice_bits, npictures, d_slice_offset,
+                                                                           d_max_length);
+    VC2B_CHECK_LAUNCH();
+    return 0;
+}
+
+int vc2b_quantize_to_fit_lists(const int32_t *d_values, const int32_t *d_quant_matrix_values, const int32_t *set_offsets,
+                               int nsets, int64_t target_size, int64_t align_bits, int minimum_qindex,
+                               int32_t *d_result, int32_t *d_quantised, void *stream)
+{
+    if (nsets < 1 || nsets > kListSets || !set_offsets || target_size < 0 || align_bits < 1) return VC2B_E_BAD_PARAMS;
+    ListArgs A;
+    memset(&A, 0, sizeof(A));
+    A.nsets = nsets;
+    for (int i = 0; i <= nsets; i++) {
+        if (set_offsets[i] < 0 || (i && set_offsets[i] < set_offsets[i - 1])) return VC2B_E_BAD_PARAMS;
+        A.set_off[i] = set_offsets[i];
+    }
+    A.target = target_size;
+    A.align = align_bits;
+    A.minimum_qindex = minimum_qindex < 0 ? 0 : minimum_qindex;
+    // at this index every int32 value quantises to zero whatever the matrix value (quant_factor >= 2^33)
+    A.max_qindex = A.minimum_qindex > 4 * 33 + 1024 ? A.minimum_qindex : 4 * 33 + 1024;
+    quantize_fit_lists_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(A, d_values, d_quant_matrix_values, d_result,
+                                                                   d_quantised);
     VC2B_CHECK_LAUNCH();
     return 0;
 }
@@ -906,24 +1139,31 @@ int64_t vc2b_packed_bytes(const vc2b_params *p, int64_t picture_bytes)
     return n;
 }
 
-int vc2b_pack_slices(const vc2b_params *p, const int32_t *d_coeffs, int npictures, int64_t picture_bytes,
-                     const int32_t *d_qindex, const int32_t *d_slice_bits, uint8_t *d_out, int64_t out_stride,
-                     void *stream)
+static int launch_pack(const vc2b_params *p, const int32_t *d_coeffs, int npictures, int64_t picture_bytes,
+                       const int32_t *d_qindex, const int32_t *d_slice_bits, const uint32_t *d_lossless_offset,
+                       uint8_t *d_out, int64_t out_stride, void *stream)
 {
     DevParams P;
     int st = make_dev_params(p, &P);
     if (st) return st;
     if (npictures <= 0) return 0;
-    const int64_t need = vc2b_packed_bytes(p, picture_bytes);
-    if (need < 0) return (int)need;
-    if (out_stride < need || (out_stride & 3)) return VC2B_E_BAD_PARAMS;
+    if (d_lossless_offset) {
+        if (P.is_ld || out_stride < 4 || (out_stride & 3)) return VC2B_E_BAD_PARAMS;
+    } else {
+        const int64_t need = vc2b_packed_bytes(p, picture_bytes);
+        if (need < 0) return (int)need;
+        if (out_stride < need || (out_stride & 3)) return VC2B_E_BAD_PARAMS;
+    }
     FitArgs F;
+    memset(&F, 0, sizeof(F));
     const long long nslices = (long long)P.slices_x * P.slices_y;
     F.total_coeff_bytes = picture_bytes - 4 * nslices;
     F.minimum_qindex = 0;
     F.max_qm = max_qm(P);
     F.stage_cap = 0;
     F.use_map = 1;
+    F.fixed_qindex = -1;
+    F.lossless_offset = d_lossless_offset;
     for (int c = 0; c < 3; c++)
         for (int b = 0; b < P.nb; b++)
             if ((long long)P.band[c][b].w * P.band[c][b].h >= (1 << 24)) F.use_map = 0;
@@ -937,6 +1177,21 @@ int vc2b_pack_slices(const vc2b_params *p, const int32_t *d_coeffs, int npicture
         P, F, d_coeffs, npictures, d_qindex, d_slice_bits, d_out, out_stride);
     VC2B_CHECK_LAUNCH();
     return 0;
+}
+
+int vc2b_pack_slices(const vc2b_params *p, const int32_t *d_coeffs, int npictures, int64_t picture_bytes,
+                     const int32_t *d_qindex, const int32_t *d_slice_bits, uint8_t *d_out, int64_t out_stride,
+                     void *stream)
+{
+    return launch_pack(p, d_coeffs, npictures, picture_bytes, d_qindex, d_slice_bits, nullptr, d_out, out_stride, stream);
+}
+
+int vc2b_pack_slices_lossless(const vc2b_params *p, const int32_t *d_coeffs, int npictures, const int32_t *d_qindex,
+                              const int32_t *d_slice_bits, const uint32_t *d_slice_offset, uint8_t *d_out,
+                              int64_t out_stride, void *stream)
+{
+    if (!d_slice_offset) return VC2B_E_BAD_PARAMS;
+    return launch_pack(p, d_coeffs, npictures, 0, d_qindex, d_slice_bits, d_slice_offset, d_out, out_stride, stream);
 }
 
 }  // extern "C"

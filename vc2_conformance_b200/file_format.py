@@ -14,7 +14,7 @@ import math
 import numpy as np
 
 from . import capi
-from .device import _ptr, _torch
+from .device import _DeviceStream, _ptr, _torch
 
 COMPONENTS = ("Y", "C1", "C2")
 
@@ -31,12 +31,14 @@ def pictures_to_raw(params, pictures, n, stream=None):
     ``[n, raw_picture_bytes]``: exactly the bytes ``write_picture`` writes for each picture."""
     torch = _torch()
     nbytes = raw_picture_bytes(params)
-    raw = torch.empty((n, nbytes), dtype=torch.uint8, device=pictures.device)
-    sp = C.c_void_p((stream or torch.cuda.current_stream(pictures.device)).cuda_stream)
-    capi.check("vc2b_pictures_to_raw",
-               capi.lib().vc2b_pictures_to_raw(C.byref(params), _ptr(pictures), n, _ptr(raw), nbytes, sp))
-    host = torch.empty((n, nbytes), dtype=torch.uint8).pin_memory()
-    host.copy_(raw, non_blocking=False)
+    # allocation, kernel and read-back all on ONE stream of the pictures' device
+    with _DeviceStream(torch, pictures.device, stream):
+        raw = torch.empty((n, nbytes), dtype=torch.uint8, device=pictures.device)
+        sp = C.c_void_p(torch.cuda.current_stream(pictures.device).cuda_stream)
+        capi.check("vc2b_pictures_to_raw",
+                   capi.lib().vc2b_pictures_to_raw(C.byref(params), _ptr(pictures), n, _ptr(raw), nbytes, sp))
+        host = torch.empty((n, nbytes), dtype=torch.uint8).pin_memory()
+        host.copy_(raw, non_blocking=False)
     return host
 
 
@@ -54,11 +56,12 @@ def read_pictures(params, file, n, device="cuda:0"):
     if len(data) != n * nbytes:
         raise EOFError("raw picture file ends early: wanted %d bytes, got %d" % (n * nbytes, len(data)))
     samples = int(capi.lib().vc2b_picture_sample_count(C.byref(params)))
-    raw = torch.frombuffer(bytearray(data), dtype=torch.uint8).to(device)
-    pictures = torch.empty(n * samples, dtype=torch.uint16, device=device)
-    sp = C.c_void_p(torch.cuda.current_stream(pictures.device).cuda_stream)
-    capi.check("vc2b_raw_to_pictures",
-               capi.lib().vc2b_raw_to_pictures(C.byref(params), _ptr(raw), nbytes, n, _ptr(pictures), sp))
+    with _DeviceStream(torch, torch.device(device), None):
+        raw = torch.frombuffer(bytearray(data), dtype=torch.uint8).to(device)
+        pictures = torch.empty(n * samples, dtype=torch.uint16, device=device)
+        sp = C.c_void_p(torch.cuda.current_stream(pictures.device).cuda_stream)
+        capi.check("vc2b_raw_to_pictures",
+                   capi.lib().vc2b_raw_to_pictures(C.byref(params), _ptr(raw), nbytes, n, _ptr(pictures), sp))
     return pictures
 
 
@@ -75,11 +78,12 @@ def compare_pictures(params, a, b, n):
     """Per picture and component: (samples that differ, PSNR in dB or None).  ``a``, ``b``: device
     uint16 tensors with ``n`` pictures each."""
     torch = _torch()
-    out = torch.zeros(n * 6, dtype=torch.int64, device=a.device)
-    sp = C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream)
-    capi.check("vc2b_picture_compare",
-               capi.lib().vc2b_picture_compare(C.byref(params), _ptr(a), _ptr(b), n, _ptr(out), sp))
-    res = out.cpu().numpy().reshape(n, 3, 2)
+    with _DeviceStream(torch, a.device, None):
+        out = torch.zeros(n * 6, dtype=torch.int64, device=a.device)
+        sp = C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream)
+        capi.check("vc2b_picture_compare",
+                   capi.lib().vc2b_picture_compare(C.byref(params), _ptr(a), _ptr(b), n, _ptr(out), sp))
+        res = out.cpu().numpy().reshape(n, 3, 2)
     dims = [(params.luma_width * params.luma_height, params.luma_depth)] + \
         [(params.color_diff_width * params.color_diff_height, params.color_diff_depth)] * 2
     return [[(int(res[i, c, 0]), psnr_from_sums(int(res[i, c, 1]), dims[c][0], (1 << dims[c][1]) - 1))

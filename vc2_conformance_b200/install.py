@@ -28,6 +28,17 @@ BINDINGS = [
     ("vc2_conformance.decoder.fragment_syntax", "dc_prediction", P.dc_prediction),
     # encoder/pictures.py:115,386: transform_and_slice_picture -> picture_encode(state, picture)
     ("vc2_conformance.encoder.pictures", "picture_encode", P.picture_encode),
+    # encoder/pictures.py:131,217,251,270,295: the per-slice quantiser functions (lists in, lists out)
+    ("vc2_conformance.encoder.pictures", "forward_quant", P.forward_quant),
+    ("vc2_conformance.encoder.pictures", "calculate_coeffs_bits", P.calculate_coeffs_bits),
+    ("vc2_conformance.encoder.pictures", "quantize_coeffs", P.quantize_coeffs),
+    ("vc2_conformance.encoder.pictures", "quantize_to_fit", P.quantize_to_fit),
+    # encoder/pictures.py:350,528,617,724 as called by make_picture_parse (:903-990): whole pictures, the
+    # coefficients stay on the device between the transform and the quantiser
+    ("vc2_conformance.encoder.pictures", "transform_and_slice_picture", P.transform_and_slice_picture),
+    ("vc2_conformance.encoder.pictures", "make_transform_data_hq_lossy", P.make_transform_data_hq_lossy),
+    ("vc2_conformance.encoder.pictures", "make_transform_data_hq_lossless", P.make_transform_data_hq_lossless),
+    ("vc2_conformance.encoder.pictures", "make_transform_data_ld_lossy", P.make_transform_data_ld_lossy),
     # the star namespace third parties use (pseudocode/__init__.py:96-107)
     ("vc2_conformance.pseudocode", "picture_decode", P.picture_decode),
     ("vc2_conformance.pseudocode", "picture_encode", P.picture_encode),
@@ -82,3 +93,11 @@ def uninstall():
 
 def installed():
     return bool(_saved)
+
+
+def original(modname, attr):
+    """The reference's own ``modname.attr``: the saved original while installed, else the live attribute."""
+    for mod, a, orig in _saved:
+        if mod.__name__ == modname and a == attr:
+            return orig
+    return getattr(importlib.import_module(modname), attr)

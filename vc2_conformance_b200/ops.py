@@ -10,7 +10,7 @@ import numpy as np
 
 from . import capi
 from .device import _ptr, _torch
-from .params import Geometry
+from .device import geometry_for as Geometry
 
 
 def _dev(a, dtype):
@@ -96,3 +96,33 @@ def dc_prediction(p, picture_coeffs, inverse=False):
     capi.check("vc2b_dc_prediction",
                capi.lib().vc2b_dc_prediction(C.byref(p), _ptr(v), 1, 1 if inverse else 0, _stream()))
     return v.cpu().numpy()
+
+
+INT64_MAX = (1 << 63) - 1
+
+
+def quantize_to_fit_lists(coeff_sets, quant_matrix_sets, target_size, align_bits=1, minimum_qindex=0):
+    """quantize_to_fit (encoder/pictures.py:295) on explicit lists: returns (qindex, [bits of each set at
+    that index], [quantised int32 array per set]).  ``target_size=None``: no search, evaluate at
+    ``minimum_qindex`` (quantize_coeffs :251 / calculate_coeffs_bits :217)."""
+    torch = _torch()
+    nsets = len(coeff_sets)
+    offs = np.zeros(nsets + 1, np.int32)
+    for i, cs in enumerate(coeff_sets):
+        offs[i + 1] = offs[i] + len(cs)
+    n = int(offs[nsets])
+    values = np.concatenate([np.asarray(cs, np.int32).reshape(-1) for cs in coeff_sets]) if n else np.zeros(0, np.int32)
+    qms = np.concatenate([np.asarray(q, np.int32).reshape(-1) for q in quant_matrix_sets]) if n else np.zeros(0, np.int32)
+    assert qms.size == values.size
+    d_v = _dev(np.append(values, 0), np.int32)
+    d_q = _dev(np.append(qms, 0), np.int32)
+    d_res = torch.zeros(16, dtype=torch.int32, device="cuda")
+    d_out = torch.zeros(n + 1, dtype=torch.int32, device="cuda")
+    target = INT64_MAX if target_size is None else int(target_size)
+    capi.check("vc2b_quantize_to_fit_lists",
+               capi.lib().vc2b_quantize_to_fit_lists(_ptr(d_v), _ptr(d_q), offs.ctypes.data_as(C.c_void_p), nsets,
+                                                     target, int(align_bits), int(minimum_qindex), _ptr(d_res),
+                                                     _ptr(d_out), _stream()))
+    res = d_res.cpu().numpy()
+    out = d_out.cpu().numpy()
+    return int(res[0]), [int(b) for b in res[1:1 + nsets]], [out[offs[i]:offs[i + 1]] for i in range(nsets)]

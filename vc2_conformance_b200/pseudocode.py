@@ -17,7 +17,8 @@ silently differing from the reference's unbounded arithmetic.
 import numpy as np
 
 from . import capi, ops
-from .params import Geometry, make_params, params_from_state
+from .device import geometry_for as Geometry
+from .params import make_params, params_from_state
 
 __all__ = [
     "EnvelopeError",
@@ -29,6 +30,9 @@ __all__ = [
     "picture_decode", "picture_encode", "inverse_wavelet_transform", "forward_wavelet_transform",
     "dc_prediction", "apply_dc_prediction", "transform_data", "DeviceTransform",
     "initialize_fragment_state", "fragment_slice",
+    "calculate_coeffs_bits", "quantize_coeffs", "quantize_to_fit", "transform_and_slice_picture",
+    "DeviceSliceCoeffs", "make_transform_data_hq_lossy", "make_transform_data_hq_lossless",
+    "make_transform_data_ld_lossy",
 ]
 
 INT32_MAX = (1 << 31) - 1
@@ -386,72 +390,6 @@ def picture_encode(state, current_picture):
 
 # ---- transform_data (decoder/transform_data_syntax.py:116) ------------------------------------------
 
-def _max_transform_bytes(p, num_slices):
-    if p.is_ld:
-        return (num_slices * p.slice_bytes_numerator) // p.slice_bytes_denominator
-    return num_slices * (p.slice_prefix_bytes + 4 + 3 * 255 * p.slice_size_scaler)
-
-
-def transform_data(state):
-    """(13.5.2) Reads every slice of the picture from ``state["_file"]`` (the reader must be byte
-    aligned, as after transform_parameters' byte_align), unpacks and dequantises on the device
-    and leaves the reader exactly after the last slice.  Raises the reference's
-    ``UnexpectedEndOfStream`` / ``InvalidSliceYLength`` and runs its per-slice level-constraint
-    checks (decoder/transform_data_syntax.py:154,222,250) when that package is importable."""
-    from .device import BatchCodec
-
-    p = params_from_state(state)
-    codec = BatchCodec(p, 1)
-    g = codec.g
-    f = state["_file"]
-    assert state["next_bit"] == 7, "transform_data must start byte aligned"
-    bound = _max_transform_bytes(p, g.num_slices)
-    first = state["current_byte"]
-    start = f.tell() - (1 if first is not None else 0)  # decoder/io.py:138 tell()
-    rest = f.read(max(bound - 1, 0)) if first is not None else b""
-    data = (bytes(bytearray([first])) if first is not None else b"") + rest
-    codec.decode_streams([data], check=False)  # (also runs the IDWT; the picture is kept for picture_decode)
-    st = codec.status_host(1)[0]
-    qindex = codec.qindex[: g.num_slices].cpu().numpy()
-    errors = _reference_errors()
-    if st[0] == capi.ST_INT32_ENVELOPE:
-        raise EnvelopeError("picture leaves the int32 envelope")
-    # per-slice level constraints, in stream order, up to the failing slice if any
-    last = int(st[1]) if st[0] != capi.ST_OK else g.num_slices
-    if errors is not None:
-        so = codec.slice_offset[: g.num_slices].cpu().numpy().astype(np.int64) & 0xffffffff
-        for n in range(min(last + 1, g.num_slices)):
-            if st[0] != capi.ST_OK and n == last and st[0] == capi.ST_UNEXPECTED_END_OF_STREAM and p.is_ld:
-                break
-            errors["assert_level_constraint"](state, "qindex", int(qindex[n]))
-            if not p.is_ld and n < last:
-                end = int(so[n + 1]) if n + 1 < g.num_slices else int(st[2])
-                errors["assert_level_constraint"](state, "total_slice_bytes", end - int(so[n]))
-    if st[0] == capi.ST_UNEXPECTED_END_OF_STREAM:
-        raise (errors["UnexpectedEndOfStream"]() if errors else EOFError("UnexpectedEndOfStream"))
-    if st[0] == capi.ST_INVALID_SLICE_Y_LENGTH:
-        n = int(st[1])
-        sy, sx = divmod(n, p.slices_x)
-        if errors:
-            raise errors["InvalidSliceYLength"](int(codec.qindex[n]), 0, sx, sy)
-        raise ValueError("InvalidSliceYLength at slice %d" % n)
-    consumed = int(st[2])
-    # leave the reader after the last slice: current_byte = next byte, next_bit = 7 (decoder/io.py:152)
-    f.seek(start + consumed)
-    byte = f.read(1)
-    state["current_byte"] = bytearray(byte)[0] if len(byte) == 1 else None
-    state["next_bit"] = 7
-    state["y_transform"] = DeviceTransform(codec, 0)
-    state["c1_transform"] = DeviceTransform(codec, 1)
-    state["c2_transform"] = DeviceTransform(codec, 2)
-    # slice_quantizers of the last slice (decoder/transform_data_syntax.py:255)
-    q = int(qindex[-1]) if g.num_slices else 0
-    state["quantizer"] = {
-        level: {orient: max(q - v, 0) for orient, v in orients.items()}
-        for level, orients in state["quant_matrix"].items()
-    }
-
-
 def _reference_errors():
     try:
         from vc2_conformance.decoder.assertions import assert_level_constraint
@@ -463,6 +401,165 @@ def _reference_errors():
         "InvalidSliceYLength": InvalidSliceYLength,
         "UnexpectedEndOfStream": UnexpectedEndOfStream,
     }
+
+
+def _raise_eos(errors):
+    raise (errors["UnexpectedEndOfStream"]() if errors else EOFError("UnexpectedEndOfStream"))
+
+
+def _intlog2(n):
+    return (n - 1).bit_length()  # pseudocode/vc2_math.py:32
+
+
+def _ld_slice_bytes(p, n):
+    """slice_bytes (pseudocode/slice_sizes.py:95) of LD slice number n."""
+    return ((n + 1) * p.slice_bytes_numerator) // p.slice_bytes_denominator - (
+        n * p.slice_bytes_numerator) // p.slice_bytes_denominator
+
+
+def _ld_slice_header(p, data, n):
+    """(qindex, slice_y_length, slice_bytes) of LD slice n read from the host bytes (ld_slice,
+    decoder/transform_data_syntax.py:145-172), or None where the bytes are not all there."""
+    s0 = (n * p.slice_bytes_numerator) // p.slice_bytes_denominator
+    nbytes = _ld_slice_bytes(p, n)
+    length_bits = _intlog2(8 * nbytes - 7)
+    hbytes = (7 + length_bits + 7) // 8
+    if s0 + hbytes > len(data):
+        return None
+    hdr = int.from_bytes(bytes(data[s0:s0 + hbytes]), "big") >> (8 * hbytes - 7 - length_bits)
+    return hdr >> length_bits, hdr & ((1 << length_bits) - 1), nbytes
+
+
+def _max_transform_bytes(p, num_slices):
+    if p.is_ld:
+        return (num_slices * p.slice_bytes_numerator) // p.slice_bytes_denominator
+    return num_slices * (p.slice_prefix_bytes + 4 + 3 * 255 * p.slice_size_scaler)
+
+
+_window_hint = {}  # parameter bytes -> bytes the last picture of these parameters took
+
+
+def _unpack_from_reader(state, p, codec):
+    """Feeds the picture's slices from the reference's reader state (decoder/io.py) to the device and
+    returns (data, status row).  The reader is left exactly after the last slice.
+
+    A seekable file is read in windows (the size of the previous picture of the same parameters plus
+    a margin, grown if the device runs out of bytes) and repositioned afterwards; any other file-like
+    object is walked slice by slice on the host, which needs no seek."""
+    g = codec.g
+    f = state["_file"]
+    assert state["next_bit"] == 7, "transform_data must start byte aligned"
+    first = state["current_byte"]
+    if first is None:
+        data = b""
+        codec.unpack_streams([data])
+        return data, codec.status_host(1)[0]
+    seekable = False
+    try:
+        seekable = bool(f.seekable())
+    except Exception:
+        pass
+    if not seekable:
+        data = bytearray()
+        try:
+            for n in range(g.num_slices):
+                data += _read_slice_bytes(state, p, n)
+        except Exception as e:  # UnexpectedEndOfStream: decode what there is, the device reports the slice
+            if type(e).__name__ not in ("UnexpectedEndOfStream", "EOFError"):
+                raise
+        codec.unpack_streams([bytes(data)])
+        return bytes(data), codec.status_host(1)[0]
+    bound = _max_transform_bytes(p, g.num_slices)
+    key = bytes(bytearray(p))
+    start = f.tell() - 1  # decoder/io.py:138 tell(): current_byte is the byte before the file position
+    want = bound if p.is_ld else min(bound, max(1 << 16, int(_window_hint.get(key, 0) * 1.25) + 4096))
+    data = bytes(bytearray([first]))
+    while True:
+        more = f.read(want - len(data))
+        data += more
+        at_eof = len(data) < want
+        codec.unpack_streams([data])
+        st = codec.status_host(1)[0]
+        if st[0] == capi.ST_UNEXPECTED_END_OF_STREAM and not at_eof and want < bound:
+            want = min(bound, 4 * want)  # the window was too small, not the stream
+            continue
+        break
+    if st[0] == capi.ST_OK:
+        consumed = int(st[2])
+        _window_hint[key] = consumed
+        # leave the reader after the last slice: current_byte = next byte, next_bit = 7 (decoder/io.py:152)
+        f.seek(start + consumed)
+        byte = f.read(1)
+        state["current_byte"] = bytearray(byte)[0] if len(byte) == 1 else None
+        state["next_bit"] = 7
+    return data, st
+
+
+def transform_data(state):
+    """(13.5.2) Reads every slice of the picture from ``state["_file"]`` (the reader must be byte
+    aligned, as after transform_parameters' byte_align), unpacks and dequantises on the device
+    and leaves the reader exactly after the last slice.  Raises the reference's
+    ``UnexpectedEndOfStream`` / ``InvalidSliceYLength`` with the reference's arguments and runs its
+    per-slice level-constraint checks (decoder/transform_data_syntax.py:154,222,250) when that package
+    is importable.  The IDWT is left to :func:`picture_decode`."""
+    p = params_from_state(state)
+    codec = _state_codec(state, p)
+    g = codec.g
+    data, st = _unpack_from_reader(state, p, codec)
+    errors = _reference_errors()
+    if st[0] == capi.ST_INT32_ENVELOPE:
+        raise EnvelopeError("picture leaves the int32 envelope")
+    qindex = codec.qindex[: g.num_slices].cpu().numpy()
+    # per-slice level constraints, in stream order, up to the failing slice if any
+    last = int(st[1]) if st[0] != capi.ST_OK else g.num_slices
+    if errors is not None:
+        check = errors["assert_level_constraint"]
+        so = codec.slice_offset[: g.num_slices].cpu().numpy().astype(np.int64) & 0xffffffff
+        for n in range(last):
+            check(state, "qindex", int(qindex[n]))
+            if not p.is_ld:
+                end = int(so[n + 1]) if n + 1 < last else _hq_slice_end(p, data, int(so[n]))
+                check(state, "total_slice_bytes", end - int(so[n]))
+        if last < g.num_slices:
+            # the failing slice: its qindex is checked if the reference got as far as reading it
+            if p.is_ld:
+                s0 = (last * p.slice_bytes_numerator) // p.slice_bytes_denominator
+                if s0 < len(data):
+                    check(state, "qindex", data[s0] >> 1)
+            else:
+                off = _hq_slice_end(p, data, int(so[last - 1])) if last > 0 else 0
+                if off is not None and off + p.slice_prefix_bytes < len(data):
+                    check(state, "qindex", data[off + p.slice_prefix_bytes])
+    if st[0] == capi.ST_UNEXPECTED_END_OF_STREAM:
+        _raise_eos(errors)
+    if st[0] == capi.ST_INVALID_SLICE_Y_LENGTH:
+        n = int(st[1])
+        sy, sx = divmod(n, p.slices_x)
+        _q, slice_y_length, nbytes = _ld_slice_header(p, data, n)
+        if errors:
+            # InvalidSliceYLength(slice_y_length, slice_bytes, sx, sy): decoder/exceptions.py:1645
+            raise errors["InvalidSliceYLength"](slice_y_length, nbytes, sx, sy)
+        raise ValueError("InvalidSliceYLength %d (slice of %d bytes) at slice %d" % (slice_y_length, nbytes, n))
+    state["y_transform"] = DeviceTransform(codec, 0)
+    state["c1_transform"] = DeviceTransform(codec, 1)
+    state["c2_transform"] = DeviceTransform(codec, 2)
+    # slice_quantizers of the last slice (decoder/transform_data_syntax.py:255)
+    q = int(qindex[-1]) if g.num_slices else 0
+    state["quantizer"] = {
+        level: {orient: max(q - v, 0) for orient, v in orients.items()}
+        for level, orients in state["quant_matrix"].items()
+    }
+
+
+def _hq_slice_end(p, data, off):
+    """Byte offset just after the HQ slice that starts at ``off`` (hq_slice,
+    decoder/transform_data_syntax.py:212-251), or None if its length bytes are not all there."""
+    pos = off + p.slice_prefix_bytes + 1
+    for _ in range(3):
+        if pos >= len(data):
+            return None
+        pos += 1 + p.slice_size_scaler * data[pos]
+    return pos
 
 
 # ---- fragmented pictures (decoder/fragment_syntax.py:140-181) ------------------------------------------
@@ -497,12 +594,17 @@ class _FragmentBuffer(object):
 
         if self._codec is None:
             codec = BatchCodec(self.p, 1)
-            codec.decode_streams([bytes(self.data)], check=False)
+            codec.unpack_streams([bytes(self.data)])
             st = codec.status_host(1)[0]
             if st[0] == capi.ST_INT32_ENVELOPE:
                 raise EnvelopeError("picture leaves the int32 envelope")
             if st[0] != capi.ST_OK:
-                raise ValueError("fragmented picture incomplete or corrupt (status %d at slice %d)" % (st[0], st[1]))
+                # truncated streams and bad slice_y_length fields were raised by fragment_slice when it read
+                # the slice, as the reference does; what is left is a picture whose slices have not all arrived
+                errors = _reference_errors()
+                if st[0] == capi.ST_UNEXPECTED_END_OF_STREAM:
+                    _raise_eos(errors)
+                raise RuntimeError("fragmented picture: device status %d at slice %d" % (st[0], st[1]))
             self._codec = codec
         return self._codec
 
@@ -526,39 +628,337 @@ def _read_bytes(state, n):
     if n == 0:
         return out
     if state["current_byte"] is None:
-        raise (errors["UnexpectedEndOfStream"]() if errors else EOFError("UnexpectedEndOfStream"))
+        _raise_eos(errors)
     out.append(state["current_byte"])
     rest = state["_file"].read(n)  # n-1 more bytes of this slice + the next current byte
     out += rest[: n - 1]
     if len(rest) < n - 1:
         state["current_byte"] = None
-        raise (errors["UnexpectedEndOfStream"]() if errors else EOFError("UnexpectedEndOfStream"))
+        _raise_eos(errors)
     state["current_byte"] = bytearray(rest)[n - 1] if len(rest) == n else None
     return out
+
+
+def _read_slice_bytes(state, p, n, check=None):
+    """The bytes of slice number n, consumed from the reader as hq_slice / ld_slice would
+    (decoder/transform_data_syntax.py:145-251); ``check(name, value)`` receives the level-constraint
+    values in the reference's order.  A stream that ends inside the slice raises UnexpectedEndOfStream
+    with the bytes read so far appended to nothing (the caller decides what to keep)."""
+    if p.is_ld:
+        nbytes = _ld_slice_bytes(p, n)
+        chunk = _read_bytes(state, nbytes)
+        if check and nbytes:
+            check("qindex", chunk[0] >> 1)
+        return chunk
+    chunk = _read_bytes(state, p.slice_prefix_bytes + 1)
+    if check:
+        check("qindex", chunk[-1])
+    for _ in range(3):
+        length = _read_bytes(state, 1)
+        chunk += length
+        chunk += _read_bytes(state, p.slice_size_scaler * length[0])
+    if check:
+        check("total_slice_bytes", len(chunk))
+    return chunk
 
 
 def fragment_slice(state, sx, sy):
     """Replacement for ``slice`` as called by fragment_data (decoder/fragment_syntax.py:168): consumes
     exactly the bytes of slice (sx, sy) and buffers them; the device unpacks the whole picture once
-    every slice is there.  Per-slice level constraints are checked like hq_slice / ld_slice do."""
+    every slice is there.  Per-slice level constraints, UnexpectedEndOfStream and InvalidSliceYLength are
+    raised here, while the slice is read, like hq_slice / ld_slice do."""
     shared = state["y_transform"].shared
+    p = shared.p
     errors = _reference_errors()
-    if (state["parse_code"] & 0xF8) == 0xC8:  # is_ld
-        n = sy * state["slices_x"] + sx
-        nbytes = ((n + 1) * state["slice_bytes_numerator"]) // state["slice_bytes_denominator"] - (
-            n * state["slice_bytes_numerator"]) // state["slice_bytes_denominator"]
-        chunk = _read_bytes(state, nbytes)
-        if errors and nbytes:
-            errors["assert_level_constraint"](state, "qindex", chunk[0] >> 1)
-    else:
-        scaler = state["slice_size_scaler"]
-        chunk = _read_bytes(state, state["slice_prefix_bytes"] + 1)
-        if errors:
-            errors["assert_level_constraint"](state, "qindex", chunk[-1])
-        for _ in range(3):
-            length = _read_bytes(state, 1)
-            chunk += length
-            chunk += _read_bytes(state, scaler * length[0])
-        if errors:
-            errors["assert_level_constraint"](state, "total_slice_bytes", len(chunk))
+    check = (lambda name, value: errors["assert_level_constraint"](state, name, value)) if errors else None
+    n = sy * state["slices_x"] + sx
+    chunk = _read_slice_bytes(state, p, n, check)
+    if p.is_ld:
+        # slice_y_length must leave room for itself (decoder/transform_data_syntax.py:166)
+        nbytes = len(chunk)
+        length_bits = _intlog2(8 * nbytes - 7)
+        hbytes = (7 + length_bits + 7) // 8
+        hdr = int.from_bytes(bytes(chunk[:hbytes]), "big") >> (8 * hbytes - 7 - length_bits)
+        slice_y_length = hdr & ((1 << length_bits) - 1)
+        if slice_y_length > 8 * nbytes - 7 - length_bits:
+            if errors:
+                raise errors["InvalidSliceYLength"](slice_y_length, nbytes, sx, sy)
+            raise ValueError("InvalidSliceYLength %d (slice of %d bytes) at slice %d" % (slice_y_length, nbytes, n))
     shared.data += chunk
+
+
+# ---- encoder: quantisation and slice assembly (encoder/pictures.py:217-792) ---------------------------
+#
+# Function-level forms (quantize_coeffs, calculate_coeffs_bits, quantize_to_fit) work on the reference's
+# Python lists through vc2b_quantize_to_fit_lists.  The whole-picture forms keep the picture's coefficients
+# on the device between transform_and_slice_picture and make_transform_data_*: one launch sequence per
+# picture instead of one call per slice.
+
+def _i32_list(values, what):
+    a = np.asarray(_to_i32(list(values), what), np.int32).reshape(-1) if len(values) else np.zeros(0, np.int32)
+    return a
+
+
+def calculate_coeffs_bits(coeffs):
+    """encoder/pictures.py:217: bits of a bounded block holding ``coeffs`` (trailing zeros are free)."""
+    v = _i32_list(coeffs, "coefficient")
+    if v.size == 0:
+        return 0
+    _q, bits, _out = ops.quantize_to_fit_lists([v], [np.zeros(v.size, np.int32)], None, 1, 0)
+    return bits[0]
+
+
+def quantize_coeffs(qindex, coeff_values, quant_matrix_values):
+    """encoder/pictures.py:251: forward_quant of every value at max(0, qindex - matrix value)."""
+    v = _i32_list(coeff_values, "coefficient")
+    if v.size == 0:
+        return []
+    qm = _i32_list(quant_matrix_values, "quantisation matrix value")[: v.size]
+    _q, _bits, out = ops.quantize_to_fit_lists([v[: qm.size]], [qm], None, 1, int(qindex))
+    return out[0].tolist()
+
+
+def quantize_to_fit(target_size, coeff_sets, align_bits=1, minimum_qindex=0):
+    """encoder/pictures.py:295: smallest qindex >= minimum_qindex at which the sets, each padded to
+    ``align_bits``, total at most ``target_size`` bits.  Returns (qindex, [quantised lists])."""
+    assert target_size >= 0
+    values = [_i32_list(cs[0], "coefficient") for cs in coeff_sets]
+    qms = [_i32_list(cs[1], "quantisation matrix value")[: v.size] for cs, v in zip(coeff_sets, values)]
+    values = [v[: q.size] for v, q in zip(values, qms)]  # zip() semantics of quantize_coeffs
+    qindex, _bits, out = ops.quantize_to_fit_lists(values, qms, int(target_size), int(align_bits),
+                                                   int(minimum_qindex))
+    return qindex, [o.tolist() for o in out]
+
+
+def _slice_order(g):
+    """Per component: (order, counts, qm) -- ``order`` lists the component's coefficient indices slice by
+    slice in bitstream order (level, orientation, then raster inside the slice's rectangle:
+    encoder/pictures.py:418-451), ``counts[slice]`` how many each slice holds, ``qm`` the quantisation
+    matrix value of every coefficient in that order."""
+    cached = getattr(g, "_slice_order", None)
+    if cached is not None:
+        return cached
+    p = g.params
+    nx, ny = p.slices_x, p.slices_y
+    nb = g.num_subbands
+    out = []
+    for c in range(3):
+        key = np.empty(g.comp_coeffs[c], np.int64)
+        qmv = np.empty(g.comp_coeffs[c], np.int32)
+        for b, band in enumerate(g.bands[c]):
+            w, h, off = band["w"], band["h"], band["off"]
+            # the slice holding column x: largest s with (w * s) // nx <= x (slice_left, slice_sizes.py:108)
+            sx = ((np.arange(w, dtype=np.int64) + 1) * nx - 1) // w
+            sy = ((np.arange(h, dtype=np.int64) + 1) * ny - 1) // h
+            key[off: off + w * h] = ((sy[:, None] * nx + sx[None, :]) * nb + b).reshape(-1)
+            qmv[off: off + w * h] = p.quant_matrix[band["level"]][band["slot"]]
+        order = np.argsort(key, kind="stable")
+        counts = np.bincount(key // nb, minlength=nx * ny)
+        out.append((order, counts, qmv[order]))
+    g._slice_order = out
+    return out
+
+
+class DeviceSliceCoeffs(list):
+    """What the device form of :func:`transform_and_slice_picture` returns: the picture's transform
+    coefficients stay in ``codec.coeffs`` (DC prediction applied for the low delay profile) for the
+    whole-picture ``make_transform_data_*`` replacements.  Anything that reads it as the reference's
+    ``[[SliceCoeffs, ...], ...]`` gets that view, built on first access."""
+
+    def __init__(self, codec, is_ld):
+        list.__init__(self)
+        self.codec = codec
+        self.is_ld = is_ld
+        self._filled = False
+
+    def _fill(self):
+        if self._filled:
+            return
+        self._filled = True
+        from vc2_conformance.encoder.pictures import ComponentCoeffs, SliceCoeffs
+
+        g = self.codec.g
+        comps = self.codec.coeff_components(0)
+        per = []
+        for c, (order, counts, qm) in enumerate(_slice_order(g)):
+            vals = comps[c][order]
+            ends = np.cumsum(counts)
+            per.append([(vals[e - n: e].tolist(), qm[e - n: e].tolist()) for e, n in zip(ends, counts)])
+        nx, ny = g.params.slices_x, g.params.slices_y
+        for sy in range(ny):
+            list.append(self, [SliceCoeffs(*(ComponentCoeffs(*per[c][sy * nx + sx]) for c in range(3)))
+                               for sx in range(nx)])
+
+    def __len__(self):
+        return self.codec.g.params.slices_y
+
+    def __getitem__(self, i):
+        self._fill()
+        return list.__getitem__(self, i)
+
+    def __iter__(self):
+        self._fill()
+        return list.__iter__(self)
+
+
+def transform_and_slice_picture(codec_features, picture):
+    """encoder/pictures.py:350 on the device: offset removal, padding, DWT (picture_encode) and, for the
+    low delay profile, apply_dc_prediction; returns a :class:`DeviceSliceCoeffs`."""
+    from vc2_conformance.encoder.pictures import get_quantization_marix
+    from vc2_conformance.pseudocode.video_parameters import set_coding_parameters
+    from vc2_data_tables import Profiles
+
+    from .device import BatchCodec
+
+    state = dict(
+        wavelet_index=codec_features["wavelet_index"],
+        wavelet_index_ho=codec_features["wavelet_index_ho"],
+        dwt_depth=codec_features["dwt_depth"],
+        dwt_depth_ho=codec_features["dwt_depth_ho"],
+        slices_x=codec_features["slices_x"],
+        slices_y=codec_features["slices_y"],
+        picture_coding_mode=codec_features["picture_coding_mode"],
+    )
+    set_coding_parameters(state, codec_features["video_parameters"])
+    state["quant_matrix"] = get_quantization_marix(codec_features)
+    is_ld = codec_features["profile"] == Profiles.low_delay
+    state["parse_code"] = 0xC8 if is_ld else 0xE8
+    if is_ld:  # placeholders: the slice sizes are only known to make_transform_data_ld_lossy
+        state["slice_bytes_numerator"] = state["slices_x"] * state["slices_y"]
+        state["slice_bytes_denominator"] = 1
+    p = params_from_state(state)
+    codec = BatchCodec(p, 1)
+    g = codec.g
+    flat = np.empty(g.picture_samples, np.uint16)
+    for c, name in enumerate(["Y", "C1", "C2"]):
+        w, h = g.dims[c]
+        a = np.array(picture[name], dtype=object)
+        if a.shape != (h, w):
+            raise ValueError("component %s is %r, expected %r" % (name, a.shape, (h, w)))
+        if a.size and (min(int(v) for v in a.reshape(-1)) < 0 or max(int(v) for v in a.reshape(-1)) > 0xffff):
+            raise EnvelopeError("sample outside the 16-bit envelope of the device pictures")
+        flat[g.plane_off[c]: g.plane_off[c] + w * h] = a.astype(np.uint16).reshape(-1)
+    codec.upload_pictures(flat[None, :])
+    codec.dwt_device(1)
+    if is_ld:
+        codec.dc_predict_device(1, inverse=True)
+    return DeviceSliceCoeffs(codec, is_ld)
+
+
+def _original(name):
+    """The reference's own function of that name (not the rebound one)."""
+    from . import install
+
+    return install.original("vc2_conformance.encoder.pictures", name)
+
+
+def _codec_with(codec, **changes):
+    """A view of ``codec`` (same device buffers) for a changed parameter set (slice sizes)."""
+    import copy
+
+    from .device import geometry_for
+    from .params import copy_params
+
+    view = copy.copy(codec)
+    view.p = copy_params(codec.p, **changes)
+    view.g = geometry_for(view.p)
+    return view
+
+
+def _per_slice_lists(g, flat_components):
+    """[comp][slice] -> list of values in bitstream order."""
+    out = []
+    for c, (order, counts, _qm) in enumerate(_slice_order(g)):
+        vals = flat_components[c][order]
+        ends = np.cumsum(counts)
+        out.append([vals[e - n: e].tolist() for e, n in zip(ends, counts)])
+    return out
+
+
+def make_transform_data_hq_lossy(picture_bytes, transform_coeffs, minimum_qindex=0, minimum_slice_size_scaler=1):
+    """encoder/pictures.py:617 for a :class:`DeviceSliceCoeffs`: one quantize_to_fit launch for every
+    slice of the picture; returns (slice_size_scaler, TransformData of HQSlice)."""
+    if not isinstance(transform_coeffs, DeviceSliceCoeffs):
+        return _original("make_transform_data_hq_lossy")(picture_bytes, transform_coeffs, minimum_qindex,
+                                                        minimum_slice_size_scaler)
+    from vc2_conformance.bitstream import HQSlice, TransformData
+    from vc2_conformance.encoder.exceptions import InsufficientHQPictureBytesError
+    from vc2_conformance.encoder.pictures import get_safe_lossy_hq_slice_size_scaler
+
+    codec0 = transform_coeffs.codec
+    num_slices = codec0.g.num_slices
+    scaler = max(get_safe_lossy_hq_slice_size_scaler(picture_bytes, num_slices), minimum_slice_size_scaler)
+    total_coeff_bytes = picture_bytes - num_slices * 4
+    if total_coeff_bytes < 0:
+        raise InsufficientHQPictureBytesError()
+    codec = _codec_with(codec0, slice_size_scaler=scaler)
+    g = codec.g
+    codec.quantize_device(1, picture_bytes, minimum_qindex)
+    qindex = codec.qindex[:num_slices].cpu().numpy()
+    bits = codec.slice_bits[: 3 * num_slices].cpu().numpy().reshape(num_slices, 3)
+    quantised = codec.quantized_host(1)[0]
+    per = _per_slice_lists(g, [quantised[g.comp_off[c]: g.comp_off[c] + g.comp_coeffs[c]] for c in range(3)])
+    align = 8 * scaler
+    den = num_slices * scaler
+    slices = []
+    for n in range(num_slices):
+        # slice_bytes (slice_sizes.py:95) in units of slice_size_scaler bytes, as at :672-690
+        total_length = ((n + 1) * total_coeff_bytes) // den - (n * total_coeff_bytes) // den
+        y_length = (int(bits[n, 0]) + align - 1) // align
+        c1_length = (int(bits[n, 1]) + align - 1) // align
+        slices.append(HQSlice(
+            qindex=int(qindex[n]), slice_y_length=y_length, slice_c1_length=c1_length,
+            slice_c2_length=total_length - y_length - c1_length,
+            y_transform=per[0][n], c1_transform=per[1][n], c2_transform=per[2][n]))
+    return scaler, TransformData(hq_slices=slices)
+
+
+def make_transform_data_hq_lossless(transform_coeffs, minimum_slice_size_scaler=1):
+    """encoder/pictures.py:528 for a :class:`DeviceSliceCoeffs`: block sizes on the device, minimal length
+    fields, the smallest slice_size_scaler that holds the longest of them."""
+    if not isinstance(transform_coeffs, DeviceSliceCoeffs):
+        return _original("make_transform_data_hq_lossless")(transform_coeffs, minimum_slice_size_scaler)
+    from vc2_conformance.bitstream import HQSlice, TransformData
+
+    codec = transform_coeffs.codec
+    g = codec.g
+    num_slices = g.num_slices
+    scaler, _ps, _offs, _totals = codec.lossless_layout(1, minimum_slice_size_scaler)
+    bits = codec.slice_bits[: 3 * num_slices].cpu().numpy().reshape(num_slices, 3)
+    per = _per_slice_lists(g, codec.coeff_components(0))
+    align = 8 * scaler
+    slices = [HQSlice(
+        qindex=0,
+        slice_y_length=(int(bits[n, 0]) + align - 1) // align,
+        slice_c1_length=(int(bits[n, 1]) + align - 1) // align,
+        slice_c2_length=(int(bits[n, 2]) + align - 1) // align,
+        y_transform=per[0][n], c1_transform=per[1][n], c2_transform=per[2][n]) for n in range(num_slices)]
+    return scaler, TransformData(hq_slices=slices)
+
+
+def make_transform_data_ld_lossy(picture_bytes, transform_coeffs, minimum_qindex=0):
+    """encoder/pictures.py:724 for a :class:`DeviceSliceCoeffs`."""
+    if not isinstance(transform_coeffs, DeviceSliceCoeffs):
+        return _original("make_transform_data_ld_lossy")(picture_bytes, transform_coeffs, minimum_qindex)
+    from vc2_conformance.bitstream import LDSlice, TransformData
+    from vc2_conformance.encoder.exceptions import InsufficientLDPictureBytesError
+
+    codec0 = transform_coeffs.codec
+    num_slices = codec0.g.num_slices
+    for n in range(num_slices):  # target_size of every slice (:752-760) must not be negative
+        target = 8 * (((n + 1) * picture_bytes) // num_slices - (n * picture_bytes) // num_slices) - 7
+        if target - _intlog2(target) < 0:
+            raise InsufficientLDPictureBytesError()
+    codec = _codec_with(codec0, slice_bytes_numerator=int(picture_bytes), slice_bytes_denominator=num_slices)
+    g = codec.g
+    codec.quantize_device(1, picture_bytes, minimum_qindex, predict=False)  # DC prediction already applied
+    qindex = codec.qindex[:num_slices].cpu().numpy()
+    bits = codec.slice_bits[: 3 * num_slices].cpu().numpy().reshape(num_slices, 3)
+    quantised = codec.quantized_host(1)[0]
+    per = _per_slice_lists(g, [quantised[g.comp_off[c]: g.comp_off[c] + g.comp_coeffs[c]] for c in range(3)])
+    slices = []
+    for n in range(num_slices):
+        c = [v for pair in zip(per[1][n], per[2][n]) for v in pair]  # interleave (:712)
+        slices.append(LDSlice(qindex=int(qindex[n]), slice_y_length=int(bits[n, 0]), y_transform=per[0][n],
+                              c_transform=c))
+    return TransformData(ld_slices=slices)
