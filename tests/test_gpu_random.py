@@ -168,9 +168,9 @@ FULL_CASES = [
                                           slices_y=270, slice_size_scaler=8)),
     # BASELINE config 5 (the encoder path): 7680x4320 12-bit 4:4:4, 240x270 slices, both filters SURVEY 8(d) names
     ("cfg5_8k_dd97_d4_444", dict(luma_width=7680, luma_height=4320, luma_depth=12, wavelet_index=0, dwt_depth=4,
-                                 slices_x=240, slices_y=270, slice_size_scaler=16)),
+                                 slices_x=240, slices_y=270, slice_size_scaler=32)),
     ("cfg5_8k_legall_d3_444", dict(luma_width=7680, luma_height=4320, luma_depth=12, wavelet_index=1, dwt_depth=3,
-                                   slices_x=240, slices_y=270, slice_size_scaler=16)),
+                                   slices_x=240, slices_y=270, slice_size_scaler=32)),
 ]
 
 
