@@ -17,7 +17,7 @@ a = ap.parse_args()
 w = bench.make_workload(a.workload, a.pictures)
 p, NP, S = w["p"], w["pictures"], w["samples"]
 codec = BatchCodec(p, NP, max_stream_bytes=NP * (w["picture_bytes"] + 64), group=a.group)
-pics = bench.synth_pictures(w, 0, min(NP, 4))
+pics = bench.synth_pictures(w, 0, 0, min(NP, 4))
 streams = codec.encode_pictures(pics, w["picture_bytes"])
 streams = [streams[i % len(streams)] for i in range(NP)]
 host, offs = codec.pack_host_streams(streams)

@@ -10,7 +10,7 @@ from vc2_conformance_b200.device import BatchCodec, _ptr
 w = bench.make_workload("cfg2", 120)
 p, NP, S = w["p"], w["pictures"], w["samples"]
 codec = BatchCodec(p, NP, max_stream_bytes=NP * (w["picture_bytes"] + 64))
-pics = bench.synth_pictures(w, 0, 4)
+pics = bench.synth_pictures(w, 0, 0, 4)
 streams = codec.encode_pictures(pics, w["picture_bytes"])
 streams = [streams[i % 4] for i in range(NP)]
 host, offs = codec.pack_host_streams(streams)

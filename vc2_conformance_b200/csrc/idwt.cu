@@ -32,7 +32,8 @@ struct LevelArgs {
     const int32_t *ll[3];
     long long ll_pic_stride[3];     // elements between consecutive pictures
     const int32_t *hb[3][3];        // HL, LH, HH (or H in slot 0 for horizontal-only levels)
-    long long hb_pic_stride;
+    long long hb_pic_stride;        // elements (int32, or int16 when hb16)
+    int32_t hb16;                   // 1: hb[][] address int16 coefficients (vc2b_unpack16's plane; wide kernel only)
     int32_t w[3], h[3];             // input LL dimensions
     // output
     int32_t *out[3];                // int32 output (intermediate LL or raw final), row stride = 2w
@@ -378,6 +379,7 @@ static int launch_level_t(const LevelArgs &A_in, int npic, cudaStream_t s)
     if constexpr (VERT && FV != 5 && Strip8Cfg<FV, FH>::kSupported && FV == FH) {
         if (level_is_wide_ok(A, npic)) return launch_wide<FV, FH>(A, npic, s);
     }
+    if (A.hb16) return VC2B_E_UNSUPPORTED;  // only the wide kernel reads int16 high-pass bands
     if constexpr (VERT) {
         using C = StripCfg<FV, FH>;
         for (int c = 0; c < A.ncomp; c++) {
@@ -438,35 +440,6 @@ static int launch_level(int fv, int fh, bool vert, const LevelArgs &A, int npic,
     }
 }
 
-// The fused kernel for the last two levels (idwt8.cuh idwt_fused2_kernel): same filter in both
-// directions, four-pair vertical window, one halo lane -- Deslauriers-Dubuc (9,7) and LeGall (5,3).
-// Opt-in (VC2B_IDWT_FUSED=1; the tests run both paths): on B200 it moves 22 % less DRAM traffic per
-// picture than the two per-level launches (ncu: 112 MB against 144 MB for the last two levels of a
-// 2160p 4:2:2 picture) but takes 41 us against 24.9 us: the per-level kernels run at 88 % of the DRAM
-// peak on their traffic, while the fused CTA is latency / issue limited (12 warps per SM in lock-step
-// with a barrier per row pair, halo recomputation in 4 of 32 lanes instead of 2, and two role code
-// paths that no longer fit the instruction cache: stall_no_instruction 2.5 per issue).
-static bool fused_pair_ok(int fv, int fh)
-{
-    const char *e = getenv("VC2B_IDWT_FUSED");
-    if (!e || atoi(e) == 0) return false;
-#ifdef VC2B_DEV_BUILD
-    return fv == 0 && fh == 0;
-#else
-    return fv == fh && (fv == 0 || fv == 1);
-#endif
-}
-
-static int launch_fused_pair(int f, const LevelArgs &A3, const LevelArgs &A4, int npic, cudaStream_t s)
-{
-    static_assert(FusedCfg<0, 0>::kSupported && FusedCfg<1, 1>::kSupported, "fused pair configuration");
-    if (f == 0) return launch_fused2<0, 0>(A3, A4, npic, s);
-#ifndef VC2B_DEV_BUILD
-    if (f == 1) return launch_fused2<1, 1>(A3, A4, npic, s);
-#endif
-    return VC2B_E_UNSUPPORTED;
-}
-
 // first high-pass band index of level n (1-based)
 static int level_first_band(const DevParams &P, int n)
 {
@@ -499,45 +472,18 @@ static void plan_scratch(const DevParams &P, int c0, int c1, ScratchPlan *sp)
     }
 }
 
-// How many pictures' worth of intermediate LL bands the last two levels keep in flight (see run_idwt).
-// VC2B_IDWT_L2_GROUP: 0 = off (every level runs over the whole group; the default), n = fixed
-// sub-group size, -1 = as many pictures as fit kL2BudgetBytes.  Measured on B200 (cfg2, 120 pictures,
-// profiles/r1_v8_idwt_l2_subgroup_sweep.txt): sub-groups of 1 / 4 / 12 pictures run at 51 / 33 / 28 us per
-// picture against 24.9 for whole-group launches -- a sub-group is less than one wave of strips, so every
-// launch costs a full strip latency and the DRAM traffic saved does not pay for it.  Kept as an
-// experiment knob (and tested); the store hints alone are worth 3 %.
-// VC2B_IDWT_L2_HINTS: bit 0 eviction hints on the stores (default), bit 1 on the loads.
-constexpr long long kL2BudgetBytes = 40LL << 20;
-
-static int l2_subgroup(long long level_out_bytes_per_picture, int npic)
-{
-    const char *e = getenv("VC2B_IDWT_L2_GROUP");  // read per call: the tests switch it
-    const int forced = e ? atoi(e) : 0;
-    if (forced == 0) return npic;
-    long long g = forced > 0 ? forced : kL2BudgetBytes / (level_out_bytes_per_picture > 0 ? level_out_bytes_per_picture : 1);
-    if (g < 1) g = 1;
-    return g < npic ? (int)g : npic;
-}
-
-// bit 0: eviction hints on the stores, bit 1: on the loads
-static int l2_hints_enabled()
-{
-    const char *e = getenv("VC2B_IDWT_L2_HINTS");
-    return e ? atoi(e) : 1;
-}
-
-// Runs all levels for components [c0, c1) of `npic` pictures.
+// Runs all levels for components [c0, c1) of `npic` pictures, one launch per level over the whole group.
+// The final level's stores carry an L2 evict_first policy (the picture is written once and never read
+// back by this library: +3 % on B200).  `coeffs16`: when not null, the high-pass bands are read from this
+// int16 plane (same element offsets as `coeffs`, which then only supplies the level-0 band).
 //
-// Level order: levels 1 .. top-2 run over the whole group (their output is small).  The last two
-// levels -- whose intermediate band is a quarter of the picture, by far the largest -- run
-// alternately over sub-groups of pictures sized to the L2 (l2_subgroup): level top-1 writes the LL
-// band of the sub-group into the SAME scratch slots every time, level top reads it straight back.
-// With the streams tagged evict_first and this band evict_last, it is produced and consumed in L2
-// and its dirty lines are overwritten by the next sub-group instead of being written back, so the
-// band does not cost a DRAM round trip ("each level is not a separate HBM pass").
-static int run_idwt(const DevParams &P, int c0, int c1, const int32_t *coeffs, long long coeff_pic_stride,
-                    int npic, uint16_t *pictures, int32_t *raw_out, int32_t *scratch, const ScratchPlan &sp,
-                    cudaStream_t s)
+// Measured and removed: keeping the band between the last two levels in L2 by running them
+// over L2-sized sub-groups of pictures, a ticket-ordered two-level launch, and a producer/consumer kernel
+// fusing the last two levels through a shared-memory ring -- all bit-exact, all slower than one launch per
+// level on B200.  What does cut the DRAM traffic of this stage is the int16 coefficient plane.
+static int run_idwt(const DevParams &P, int c0, int c1, const int32_t *coeffs, const int16_t *coeffs16,
+                    long long coeff_pic_stride, int npic, uint16_t *pictures, int32_t *raw_out, int32_t *scratch,
+                    const ScratchPlan &sp, cudaStream_t s)
 {
     const int top = P.dwt_depth + P.dwt_depth_ho;
     const int ncomp = c1 - c0;
@@ -546,6 +492,7 @@ static int run_idwt(const DevParams &P, int c0, int c1, const int32_t *coeffs, l
     memset(&A, 0, sizeof(A));
     A.ncomp = ncomp;
     A.hb_pic_stride = coeff_pic_stride;
+    A.hb16 = coeffs16 ? 1 : 0;
     A.pic_pic_stride = P.pic_samples;
     A.shift = get_filter(P.wavelet_index_ho).shift;
     for (int i = 0; i < ncomp; i++) {
@@ -571,36 +518,33 @@ static int run_idwt(const DevParams &P, int c0, int c1, const int32_t *coeffs, l
         VC2B_CHECK_LAUNCH();
         return 0;
     }
-    const bool hints = (l2_hints_enabled() & 1) && npic > 1;
-    A.hint_loads = (l2_hints_enabled() & 2) && npic > 1;
-    // Level n over pictures [first, first + cnt): its LL input sits in scratch slots ll_slot.. (or in
-    // the coefficients for n == 1), its output goes to scratch slots out_slot..
-    auto fill_level = [&](int n, int first, int ll_slot, int out_slot, bool resident_out) {
+    for (int n = 1; n <= top; n++) {
+        // Level n: its LL input is what level n-1 wrote (the coefficients for n == 1); ping-pong: level n
+        // writes scratch region ((top-1)-n)%2 (0 = a)
         const bool vert = n > P.dwt_depth_ho;
         const bool last = n == top;
         const int fb = level_first_band(P, n);
-        // ping-pong: level n writes region ((top-1)-n)%2 (0 = a), reads what level n-1 wrote
         const int wsel = ((top - 1) - n) & 1;
         for (int i = 0; i < ncomp; i++) {
             const int c = c0 + i;
             const Band &B = P.band[c][fb];
             A.w[i] = B.w;
             A.h[i] = B.h;
-            for (int k = 0; k < (vert ? 3 : 1); k++)
-                A.hb[i][k] = coeffs + (long long)first * coeff_pic_stride + P.comp_off[c] + P.band[c][fb + k].off;
-            A.pic[i] = pictures ? pictures + (long long)first * P.pic_samples + P.pic_off[c] : nullptr;
+            for (int k = 0; k < (vert ? 3 : 1); k++) {
+                const long long off = (long long)P.comp_off[c] + P.band[c][fb + k].off;
+                A.hb[i][k] = coeffs16 ? reinterpret_cast<const int32_t *>(coeffs16 + off) : coeffs + off;
+            }
+            A.pic[i] = pictures ? pictures + P.pic_off[c] : nullptr;
             if (n == 1) {
-                A.ll[i] = coeffs + (long long)first * coeff_pic_stride + P.comp_off[c] + P.band[c][0].off;
+                A.ll[i] = coeffs + P.comp_off[c] + P.band[c][0].off;
                 A.ll_pic_stride[i] = coeff_pic_stride;
             } else {
                 const int rsel = ((top - 1) - (n - 1)) & 1;
-                A.ll[i] = scratch + (long long)ll_slot * scratch_pic +
-                          (rsel == 0 ? sp.comp_off_a[c] : sp.size_a + sp.comp_off_b[c]);
+                A.ll[i] = scratch + (rsel == 0 ? sp.comp_off_a[c] : sp.size_a + sp.comp_off_b[c]);
                 A.ll_pic_stride[i] = scratch_pic;
             }
             if (!last) {
-                A.out[i] = scratch + (long long)out_slot * scratch_pic +
-                           (wsel == 0 ? sp.comp_off_a[c] : sp.size_a + sp.comp_off_b[c]);
+                A.out[i] = scratch + (wsel == 0 ? sp.comp_off_a[c] : sp.size_a + sp.comp_off_b[c]);
                 A.out_pic_stride[i] = scratch_pic;
             } else {
                 A.out[i] = raw_out;
@@ -608,54 +552,43 @@ static int run_idwt(const DevParams &P, int c0, int c1, const int32_t *coeffs, l
             }
         }
         A.final_u16 = (last && pictures) ? 1 : 0;
-        A.hint_hb = A.hint_loads ? kL2EvictFirst : kL2Normal;               // read once
-        A.hint_ll = (A.hint_loads && n == 1) ? kL2EvictFirst : kL2Normal;   // level-0 band: read once
-        A.hint_out = !hints ? kL2Normal : (last ? kL2EvictFirst : (resident_out ? kL2EvictLast : kL2Normal));
-    };
-    auto run_level = [&](int n, int first, int cnt, int ll_slot, int out_slot, bool resident_out) -> int {
-        fill_level(n, first, ll_slot, out_slot, resident_out);
-        return launch_level(P.wavelet_index, P.wavelet_index_ho, n > P.dwt_depth_ho, A, cnt, s);
-    };
-    // last two levels in one kernel, the band between them staying on chip
-    if (pictures && P.dwt_depth >= 2 && fused_pair_ok(P.wavelet_index, P.wavelet_index_ho)) {
-        fill_level(top - 1, 0, 0, 0, false);
-        const LevelArgs A3 = A;
-        fill_level(top, 0, 0, 0, false);
-        const LevelArgs A4 = A;
-        if (level_is_wide_ok(A3, npic) && level_is_wide_ok(A4, npic)) {
-            for (int n = 1; n <= top - 2; n++) {
-                int st = run_level(n, 0, npic, 0, 0, false);
-                if (st) return st;
-            }
-            return launch_fused_pair(P.wavelet_index, A3, A4, npic, s);
-        }
-    }
-    long long out_bytes = 0;  // level top-1 output per picture
-    if (top >= 2)
-        for (int i = 0; i < ncomp; i++) {
-            const Band &B = P.band[c0 + i][level_first_band(P, top)];
-            out_bytes += 4LL * B.w * B.h;
-        }
-    const int sub = top >= 2 ? l2_subgroup(out_bytes, npic) : npic;
-    if (sub >= npic) {
-        for (int n = 1; n <= top; n++) {
-            int st = run_level(n, 0, npic, 0, 0, npic == 1 ? false : (n == top - 1 && out_bytes * npic <= kL2BudgetBytes));
-            if (st) return st;
-        }
-        return 0;
-    }
-    for (int n = 1; n <= top - 2; n++) {
-        int st = run_level(n, 0, npic, 0, 0, false);
-        if (st) return st;
-    }
-    for (int first = 0; first < npic; first += sub) {
-        const int cnt = npic - first < sub ? npic - first : sub;
-        int st = run_level(top - 1, first, cnt, first, 0, true);
-        if (st) return st;
-        st = run_level(top, first, cnt, 0, 0, false);
+        A.hint_loads = 0;
+        A.hint_hb = A.hint_ll = kL2Normal;
+        A.hint_out = (last && npic > 1) ? kL2EvictFirst : kL2Normal;
+        const int st = launch_level(P.wavelet_index, P.wavelet_index_ho, vert, A, npic, s);
         if (st) return st;
     }
     return 0;
+}
+
+// Whether every level of this parameter set runs on the wide kernel with vector-aligned bands: the
+// condition for the int16 coefficient plane (vc2b_unpack16 / vc2b_idwt16).
+static bool coeff16_transform_ok(const DevParams &P)
+{
+    if (P.dwt_depth_ho != 0 || P.dwt_depth < 1) return false;
+    int f = P.wavelet_index, fh = P.wavelet_index_ho;
+    if (f == 4) f = 3;
+    if (fh == 4) fh = 3;
+    if (f != fh) return false;
+    bool wide = false;
+    switch (f) {
+    case 0: wide = Strip8Cfg<0, 0>::kSupported; break;
+#ifndef VC2B_DEV_BUILD
+    case 1: wide = Strip8Cfg<1, 1>::kSupported; break;
+    case 2: wide = Strip8Cfg<2, 2>::kSupported; break;
+    case 3: wide = Strip8Cfg<3, 3>::kSupported; break;
+    case 6: wide = Strip8Cfg<6, 6>::kSupported; break;
+#endif
+    default: wide = false;
+    }
+    if (!wide) return false;
+    if (P.pic_coeffs % kWideNP) return false;
+    for (int c = 0; c < 3; c++) {
+        if (P.comp_off[c] % kWideNP) return false;
+        for (int b = 0; b < P.nb; b++)
+            if (P.band[c][b].w % kWideNP || P.band[c][b].off % kWideNP) return false;
+    }
+    return true;
 }
 
 }  // namespace vc2b
@@ -691,8 +624,42 @@ int vc2b_idwt(const vc2b_params *p, const int32_t *d_coeffs, int npictures, uint
     if (group > npictures) group = npictures;
     for (int i = 0; i < npictures; i += group) {
         const int n = (npictures - i < group) ? npictures - i : group;
-        st = run_idwt(P, 0, 3, d_coeffs + (long long)i * P.pic_coeffs, P.pic_coeffs, n,
+        st = run_idwt(P, 0, 3, d_coeffs + (long long)i * P.pic_coeffs, nullptr, P.pic_coeffs, n,
                       d_pictures + (long long)i * P.pic_samples, nullptr, (int32_t *)d_scratch, sp,
+                      (cudaStream_t)stream);
+        if (st) return st;
+    }
+    return 0;
+}
+
+int vc2b_coeff16_supported(const vc2b_params *p)
+{
+    DevParams P;
+    if (make_dev_params(p, &P)) return 0;
+    return coeff16_transform_ok(P) && lanes_unpack_ok(P) ? 1 : 0;
+}
+
+int vc2b_idwt16(const vc2b_params *p, const int32_t *d_coeffs, const int16_t *d_coeffs16, int npictures,
+                uint16_t *d_pictures, void *d_scratch, int64_t scratch_bytes, void *stream)
+{
+    DevParams P;
+    int st = make_dev_params(p, &P);
+    if (st) return st;
+    if (!coeff16_transform_ok(P) || !d_coeffs16) return VC2B_E_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(d_coeffs) & 15) || (reinterpret_cast<uintptr_t>(d_coeffs16) & 15) ||
+        (reinterpret_cast<uintptr_t>(d_scratch) & 15))
+        return VC2B_E_BAD_PARAMS;
+    if (npictures <= 0) return 0;
+    ScratchPlan sp;
+    plan_scratch(P, 0, 3, &sp);
+    const long long per_pic = (sp.size_a + sp.size_b) * (long long)sizeof(int32_t);
+    int group = per_pic > 0 ? (int)(scratch_bytes / per_pic) : npictures;
+    if (group < 1) return VC2B_E_SCRATCH_TOO_SMALL;
+    if (group > npictures) group = npictures;
+    for (int i = 0; i < npictures; i += group) {
+        const int n = (npictures - i < group) ? npictures - i : group;
+        st = run_idwt(P, 0, 3, d_coeffs + (long long)i * P.pic_coeffs, d_coeffs16 + (long long)i * P.pic_coeffs,
+                      P.pic_coeffs, n, d_pictures + (long long)i * P.pic_samples, nullptr, (int32_t *)d_scratch, sp,
                       (cudaStream_t)stream);
         if (st) return st;
     }
@@ -710,8 +677,8 @@ int vc2b_idwt_raw(const vc2b_params *p, int comp, const int32_t *d_coeffs, int32
     plan_scratch(P, comp, comp + 1, &sp);
     if ((sp.size_a + sp.size_b) * (long long)sizeof(int32_t) > scratch_bytes) return VC2B_E_SCRATCH_TOO_SMALL;
     // d_coeffs points at the component's own coefficients
-    return run_idwt(P, comp, comp + 1, d_coeffs - P.comp_off[comp], 0, 1, nullptr, d_out, (int32_t *)d_scratch,
-                    sp, (cudaStream_t)stream);
+    return run_idwt(P, comp, comp + 1, d_coeffs - P.comp_off[comp], nullptr, 0, 1, nullptr, d_out,
+                    (int32_t *)d_scratch, sp, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -1074,21 +1074,21 @@ int vc2b_unpack(const vc2b_params *p, const uint8_t *d_data, const int64_t *d_pi
     if (lanes) {
         const long long tasks = (long long)npictures * ((P.slices_x * P.slices_y + 31) / 32);
         long long nblk = (tasks + kLaneWarps - 1) / kLaneWarps;
-        // persistent: 6 CTAs per SM are resident (80 registers, 25 KB shared each).  VC2B_UNPACK_CTAS_PER_SM
-        // (1..6) leaves room on every SM for a kernel of another stream (tools/try_overlap.py).
-        long long per_sm = 6;
-        if (const char *e = getenv("VC2B_UNPACK_CTAS_PER_SM")) {
-            const int v = atoi(e);
-            if (v >= 1 && v <= 6) per_sm = v;
-        }
-        const long long max_blocks = 148LL * per_sm;
+        // persistent: two CTAs of twelve warps per SM (the two-code table is 32 KB per CTA)
+        const long long max_blocks = 148LL * 2;
         if (nblk > max_blocks) nblk = max_blocks;
-        if (P.is_ld)
-            unpack_lanes_kernel<true><<<(unsigned)nblk, kLaneWarps * 32, 0, s>>>(P, d_data, d_pic_offset, npictures,
-                                                                                 nullptr, d_coeffs, d_qindex, d_status);
-        else
-            unpack_lanes_kernel<false><<<(unsigned)nblk, kLaneWarps * 32, 0, s>>>(
+        // the attribute is per device: set at every launch (a process may drive several GPUs)
+        if (P.is_ld) {
+            cudaFuncSetAttribute(unpack_lanes_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)kLaneSmemBytes);
+            unpack_lanes_kernel<true><<<(unsigned)nblk, kLaneWarps * 32, kLaneSmemBytes, s>>>(
+                P, d_data, d_pic_offset, npictures, nullptr, d_coeffs, d_qindex, d_status);
+        } else {
+            cudaFuncSetAttribute(unpack_lanes_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)kLaneSmemBytes);
+            unpack_lanes_kernel<false><<<(unsigned)nblk, kLaneWarps * 32, kLaneSmemBytes, s>>>(
                 P, d_data, d_pic_offset, npictures, d_slice_offset, d_coeffs, d_qindex, d_status);
+        }
         VC2B_CHECK_LAUNCH();
     } else {
         const long long warps = (long long)npictures * P.slices_x * P.slices_y;

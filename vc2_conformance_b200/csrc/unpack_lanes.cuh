@@ -22,19 +22,23 @@
 
 namespace vc2b {
 
-constexpr int kLaneWarps = 4;            // warps per CTA
+constexpr int kLaneWarps = 12;           // warps per CTA (two CTAs per SM share the tables of LaneBlock)
+constexpr int kPairBits = 12;            // window of the two-code look-up table
+constexpr int kPairEntries = 1 << kPairBits;
+constexpr uint32_t kPairMaxQf = (1u << 26) - 1;  // 30 * qf + quant_offset + 2 < 2^31
 constexpr int kLaneBands = 16;           // subbands per component this kernel supports
 constexpr int kLaneMaxCoef = 512;        // coefficients per slice component this kernel supports
 constexpr int kLaneBaseStride = kLaneBands + 1;
 constexpr int kLaneChunk = 16;           // codes per lane between two store phases
 constexpr int kLaneTS = 34;              // tile row stride: conflict-free for both access patterns
 
-struct LaneWarp {                        // per-warp shared memory
+struct __align__(16) LaneWarp {          // per-warp shared memory
     int32_t tile[kLaneChunk * kLaneTS];  // [code of the chunk][slice]
     int32_t base[32 * kLaneBaseStride];  // [slice][band]: offset of the rectangle in the component
+    uint4 stage[2][32];                  // [slot][lane]: the lane's bitstream, 16 bytes per slot (lane_fetch)
 };
 
-struct LaneBlock {                       // per-CTA shared memory
+struct __align__(16) LaneBlock {                       // per-CTA shared memory
     uint32_t map[2][kLaneMaxCoef];       // [luma, chroma]: coefficient -> band << 26 | y * stride + x
     int32_t ref_w[2][kLaneBands];        // rectangle of slice (0, 0): floor(band / slices)
     int32_t ref_h[2][kLaneBands];
@@ -44,6 +48,7 @@ struct LaneBlock {                       // per-CTA shared memory
     int32_t ref_ncoef[2];
     uint32_t slut[256];                  // 8-bit window -> 2^length | magnitude << 16 | sign << 30 (0: longer code)
     uint2 qtab[kQTab];
+    uint32_t plut[kPairEntries];         // 12-bit window -> the next TWO codes (build_pair_lut)
 };
 
 // Codes that fit an 8-bit window, sign included: 0 -> "1"; +-1..2 -> 4 bits; +-3..6 -> 6 bits;
@@ -78,21 +83,99 @@ __device__ __forceinline__ void build_lane_lut(uint32_t *slut, int tid, int nthr
     }
 }
 
+// The next TWO codes of a 12-bit window in one look-up (decoder/io.py:285-313 applied twice).  At the bit
+// rates of the BASELINE streams 59 % of the codes are the single bit "1" (zero) and 37 % have four bits
+// (+-1, +-2): two consecutive codes fit twelve bits unless one of them has ten bits or more, so the
+// lanes of a warp stay in lockstep at two codes per look-up and a step in which some lane's pair does not
+// fit (entry 0) falls back to the one-code path for the whole warp.
+//   byte 0 = bits consumed by both codes (1..12) | sign 2 << 6, byte 1 = magnitude 1, byte 2 = magnitude 2,
+//   byte 3 = sign 1 << 6; signs are two-bit signed numbers (+1, 0, -1), magnitudes are <= 30.
+// 32-bit entries: one shared-memory wavefront per look-up when the lanes hit different banks (the LSU data
+// pipe is the busiest unit of this kernel).
+__device__ __forceinline__ void build_pair_lut(uint32_t *plut, int tid, int nthreads)
+{
+    for (int e = tid; e < kPairEntries; e += nthreads) {
+        int pos = kPairBits - 1;
+        uint32_t mag[2] = {0, 0}, sgn[2] = {0, 0};
+        bool complete = true;
+        for (int c = 0; c < 2 && complete; c++) {
+            uint32_t value = 1;
+            bool stop = false;
+            while (pos >= 0) {
+                const int follow = (e >> pos) & 1;
+                pos--;
+                if (follow) { stop = true; break; }
+                if (pos < 0) break;
+                value = (value << 1) | ((e >> pos) & 1);
+                pos--;
+            }
+            if (!stop) { complete = false; break; }
+            value -= 1;
+            if (value) {
+                if (pos < 0) { complete = false; break; }
+                sgn[c] = ((e >> pos) & 1) ? 3u : 1u;
+                pos--;
+            }
+            mag[c] = value;
+        }
+        uint32_t entry = 0;
+        if (complete) {
+            const uint32_t used = (uint32_t)(kPairBits - 1 - pos);
+            entry = used | (sgn[1] << 6) | (mag[0] << 8) | (mag[1] << 16) | (sgn[0] << 30);
+        }
+        plut[e] = entry;
+    }
+}
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
+{
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+// The bitstream of a lane reaches it through shared memory: two lane-private 16-byte slots filled by
+// cp.async, one piece ahead of the one being read.  (Per-lane 4-byte global loads were the largest stall of
+// this kernel -- every load touches 32 different L1 lines and its scoreboard had to be waited for at the
+// top of every group of codes; a cp.async group is waited for four refills after it was issued.)
+constexpr int kLaneSlotStride = 32 * 16;  // bytes between the two slots of a lane
+
 struct LaneReader {
-    const uint32_t *wp;   // next word to load
+    const uint4 *cp;      // next 16-byte piece of the stream to stage
     uint64_t buf;         // bit buffer, next bit at the top; bits below `avail` are zero
-    uint32_t ahead;       // the word after the buffer as loaded (raw), fetched one refill early so
-                          // that the load latency is hidden; it is only looked at by the next refill
+    uint32_t ahead;       // the word after the buffer (raw), read from the slots one refill early
+    uint32_t slot;        // shared-memory address of the lane's first slot
+    uint32_t wi;          // next word to read from the slots (bit 2: slot, bits 0-1: word)
     int avail;            // valid bits in buf
-    int remaining;        // bits of the bounded block at and after *wp (<= 0: past its end)
+    int remaining;        // bits of the bounded block at and after word wi (<= 0: past its end)
 };
 
-// Issues the load of the next word of the block (nothing is loaded past its end).
+__device__ __forceinline__ void lane_stage(uint32_t dst, const uint4 *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+__device__ __forceinline__ uint32_t lane_word_addr(const LaneReader &R, uint32_t i)
+{
+    return R.slot + ((i & 4u) << 7) + ((i & 3u) << 2);
+}
+
+// Takes the next word of the block into `ahead` (nothing is read past its end) and, when that was the
+// last word of a slot, stages the piece after the other slot's into it.
 __device__ __forceinline__ void lane_fetch(LaneReader &R)
 {
-    if (R.remaining > 0) R.ahead = __ldg(R.wp);
-    R.wp++;
+    // every group but the newest is complete: the newest fills the slot that is not being read
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    if (R.remaining > 0) R.ahead = lds_u32(lane_word_addr(R, R.wi));
+    R.wi++;
     R.remaining -= 32;
+    if ((R.wi & 3u) == 0) {
+        if (R.remaining > 128) {
+            lane_stage(R.slot + (((R.wi & 4u) ^ 4u) << 7), R.cp);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        R.cp++;
+    }
 }
 
 // The word fetched last as 32 bits of the bounded block: ones past its end (decoder/io.py:246-252).
@@ -113,27 +196,45 @@ __device__ __forceinline__ void lane_refill(LaneReader &R)
     }
 }
 
-__device__ __forceinline__ void lane_reader_init(LaneReader &R, const uint8_t *blk, int bit_off, long long nbits,
-                                                 bool active)
+// `slot`: shared-memory address of the lane's staging slots (LaneWarp::stage).  Reads whole 16-byte pieces:
+// up to 15 bytes before the block and 47 bytes after its start, inside the stream buffer and its slack.
+__device__ __forceinline__ void lane_reader_init(LaneReader &R, uint32_t slot, const uint8_t *blk, int bit_off,
+                                                 long long nbits, bool active)
 {
     const uintptr_t addr = reinterpret_cast<uintptr_t>(blk);
-    R.wp = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
+    R.cp = reinterpret_cast<const uint4 *>(addr & ~(uintptr_t)15);
+    R.slot = slot;
+    const uint32_t w0 = (uint32_t)(addr & 15) >> 2;
     const int skip = (int)(addr & 3) * 8 + bit_off;   // <= 31
     long long rem = nbits + skip;
     if (rem > (1LL << 30)) rem = 1LL << 30;           // a slice of this kernel never reads that far
     R.remaining = active ? (int)rem : 0;
-    // the first three words are fetched together (one load latency, not three)
+    // the first two pieces are staged together (one load latency); they hold the first three words
+    if (R.remaining > 0) {
+        lane_stage(slot, R.cp);
+        lane_stage(slot + kLaneSlotStride, R.cp + 1);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    R.cp += 2;
     uint32_t raw0 = 0, raw1 = 0;
     R.ahead = 0;
-    if (R.remaining > 0) raw0 = __ldg(R.wp);
-    if (R.remaining > 32) raw1 = __ldg(R.wp + 1);
-    if (R.remaining > 64) R.ahead = __ldg(R.wp + 2);
-    uint32_t w0 = __byte_perm(raw0, 0, 0x0123), w1 = __byte_perm(raw1, 0, 0x0123);
-    if (R.remaining < 32) w0 |= 0xffffffffu >> max(R.remaining, 0);
-    if (R.remaining < 64) w1 |= 0xffffffffu >> max(R.remaining - 32, 0);
-    R.wp += 3;
+    if (R.remaining > 0) raw0 = lds_u32(lane_word_addr(R, w0));
+    if (R.remaining > 32) raw1 = lds_u32(lane_word_addr(R, w0 + 1));
+    if (R.remaining > 64) R.ahead = lds_u32(lane_word_addr(R, w0 + 2));
+    uint32_t wd0 = __byte_perm(raw0, 0, 0x0123), wd1 = __byte_perm(raw1, 0, 0x0123);
+    if (R.remaining < 32) wd0 |= 0xffffffffu >> max(R.remaining, 0);
+    if (R.remaining < 64) wd1 |= 0xffffffffu >> max(R.remaining - 32, 0);
+    R.wi = w0 + 3;
     R.remaining -= 96;
-    R.buf = (((uint64_t)w0 << 32) | w1) << skip;
+    if (R.wi >= 4) {  // the first slot is used up already: stage the third piece into it
+        if (R.remaining > 32 * (int)(8 - R.wi)) {
+            lane_stage(slot, R.cp);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        R.cp++;
+    }
+    R.buf = (((uint64_t)wd0 << 32) | wd1) << skip;
     R.avail = 64 - skip;
 }
 
@@ -205,10 +306,13 @@ __device__ __noinline__ LaneLong lane_read_long_cold(LaneReader R)
     return o;
 }
 
-__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
+// Byte `B` of x, sign extended (prmt in its default mode replicates the sign bit of the selected byte when
+// bit 3 of a selector nibble is set; __byte_perm masks that bit away).
+template <int B>
+__device__ __forceinline__ int prmt_sext(uint32_t x)
 {
-    uint32_t v;
-    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    int v;
+    asm("prmt.b32 %0, %1, %1, %2;" : "=r"(v) : "r"(x), "n"(0x8880 + B + 0x1110 * B));
     return v;
 }
 
@@ -287,7 +391,7 @@ __device__ __forceinline__ void lanes_block(const DevParams &P, const int comp, 
     const bool my_match = match || !active;
 
     LaneReader R;
-    lane_reader_init(R, blk, bit_off, nbits, active);
+    lane_reader_init(R, (uint32_t)__cvta_generic_to_shared(&W.stage[0][lane]), blk, bit_off, nbits, active);
 
     int b = -1, next = 0;
     uint32_t qf = 0, qo = 0, maxmag = 0;
@@ -316,26 +420,31 @@ __device__ __forceinline__ void lanes_block(const DevParams &P, const int comp, 
         mark = 1;                                                                                    \
     }
 
+    // the band of code j0 + i starts here (slice_quantizers, transform_data_syntax.py:255)
+#define VC2B_LANE_NEXT_BAND(i)                                                                       \
+    {                                                                                                \
+        VC2B_LANE_CLOSE_BAND()                                                                       \
+        do {                                                                                         \
+            b++;                                                                                     \
+            int cnt = S.ref_cnt[mc][b];                                                              \
+            if (!my_match) {                                                                         \
+                const uint32_t wh = lane_rect_wh(P.band[comp][b].w, P.band[comp][b].h, P.slices_x,   \
+                                                 P.slices_y, sx, sy);                                \
+                cnt = (int)(wh & 0xffffu) * (int)(wh >> 16);                                         \
+            }                                                                                        \
+            next += cnt << I;                                                                        \
+        } while (j0 + (i) == next);                                                                  \
+        const int q = max(qindex - P.band[comp][b].qm, 0);                                           \
+        const uint2 qq = S.qtab[min(q, kQTab - 1)];                                                  \
+        qf = qq.x;                                                                                   \
+        qo = qq.y;                                                                                   \
+        qfast = qf <= kPairMaxQf;                                                                    \
+    }
+
     // one code: read_sintb + inverse_quant, value to tile row i
 #define VC2B_LANE_STEP(i, CHK)                                                                       \
     {                                                                                                \
-        if (CHK && j0 + (i) == next) {  /* next band (slice_quantizers, transform_data_syntax.py:255) */ \
-            VC2B_LANE_CLOSE_BAND()                                                                   \
-            do {                                                                                     \
-                b++;                                                                                 \
-                int cnt = S.ref_cnt[mc][b];                                                          \
-                if (!my_match) {                                                                     \
-                    const uint32_t wh = lane_rect_wh(P.band[comp][b].w, P.band[comp][b].h, P.slices_x, \
-                                                     P.slices_y, sx, sy);                            \
-                    cnt = (int)(wh & 0xffffu) * (int)(wh >> 16);                                     \
-                }                                                                                    \
-                next += cnt << I;                                                                    \
-            } while (j0 + (i) == next);                                                              \
-            const int q = max(qindex - P.band[comp][b].qm, 0);                                       \
-            const uint2 qq = S.qtab[min(q, kQTab - 1)];                                              \
-            qf = qq.x;                                                                               \
-            qo = qq.y;                                                                               \
-        }                                                                                            \
+        if (CHK && j0 + (i) == next) VC2B_LANE_NEXT_BAND(i)                                          \
         const uint32_t hi = (uint32_t)(R.buf >> 32);                                                 \
         const uint32_t e = lds_u32(slut_addr + 4 * (hi >> 24));                                      \
         const uint32_t M = e & 0x1ffu;                                                               \
@@ -361,22 +470,50 @@ __device__ __forceinline__ void lanes_block(const DevParams &P, const int comp, 
         tile[(i) * kLaneTS] = (int32_t)t * sgn;                                                      \
     }
 
+    // Two codes per look-up (build_pair_lut).  The magnitudes are at most 30 and the lane's quantiser factor
+    // is below 2^26 (qfast), so m*qf + qo stays below 2^31: 32-bit arithmetic, no envelope bookkeeping beyond
+    // the largest magnitude of the band.
+#define VC2B_LANE_PAIR_VALUE(i, m, sg)                                                               \
+    tile[(i) * kLaneTS] = (int32_t)(((m) * qf + qo) >> 2) * (sg);
+
     // the int32 envelope was left if some m*qf+qo reached 2^33 (hiacc >= 2), a non-zero value met a
     // saturated quantiser or a value had 32 or more data bits (bad != 0)
     uint32_t hiacc = 0, bad = 0, mark = 1;
+    bool qfast = false;
+    uint32_t plut_addr = (uint32_t)__cvta_generic_to_shared(S.plut);
+    asm volatile("" : "+r"(plut_addr));
     const int c = lane & 15, h = lane >> 4;   // store phase: half-warp h takes slice 2k+h, lane c its code c
     for (int j0 = 0; j0 < jmax; j0 += kLaneChunk) {
         // ---- decode: lane = slice, kLaneChunk codes each -------------------------------------------
         if (uniform && j0 + kLaneChunk <= refcodes) {
 #pragma unroll 1
             for (int g = 0; g < kLaneChunk / 4; g++) {
+                if (j0 == next) VC2B_LANE_NEXT_BAND(0)  // a band starts with this group
                 if (next - j0 >= 4) {  // no band starts within these four codes
-                    VC2B_LANE_STEP(0, false)
-                    VC2B_LANE_STEP(1, false)
-                    VC2B_LANE_STEP(2, false)
-                    VC2B_LANE_STEP(3, false)
+                    // two look-ups of two codes each; mark == 1 here, avail >= 33
+                    const uint32_t ea = lds_u32(plut_addr + (((uint32_t)(R.buf >> 32) >> (32 - kPairBits)) << 2));
+                    const uint32_t la = ea & 15u;
+                    const uint64_t bufa = R.buf << la;
+                    const uint32_t eb = lds_u32(plut_addr + (((uint32_t)(bufa >> 32) >> (32 - kPairBits)) << 2));
+                    const uint32_t lb = eb & 15u;
+                    if (__all_sync(0xffffffffu, qfast && la * lb != 0)) {
+                        R.buf = bufa << lb;
+                        R.avail -= (int)(la + lb);
+                        const uint32_t ma1 = __byte_perm(ea, 0, 0x4441), ma2 = __byte_perm(ea, 0, 0x4442);
+                        const uint32_t mb1 = __byte_perm(eb, 0, 0x4441), mb2 = __byte_perm(eb, 0, 0x4442);
+                        VC2B_LANE_PAIR_VALUE(0, ma1, __mulhi((int)ea, 4))
+                        VC2B_LANE_PAIR_VALUE(1, ma2, __mulhi((int)(ea << 24), 4))
+                        VC2B_LANE_PAIR_VALUE(2, mb1, __mulhi((int)eb, 4))
+                        VC2B_LANE_PAIR_VALUE(3, mb2, __mulhi((int)(eb << 24), 4))
+                        maxmag = max(max(maxmag, max(ma1, ma2)), max(mb1, mb2));
+                    } else {
+                        VC2B_LANE_STEP(0, false)
+                        VC2B_LANE_STEP(1, false)
+                        VC2B_LANE_STEP(2, false)
+                        VC2B_LANE_STEP(3, false)
+                    }
                 } else {
-                    VC2B_LANE_STEP(0, true)
+                    VC2B_LANE_STEP(0, false)
                     VC2B_LANE_STEP(1, true)
                     VC2B_LANE_STEP(2, true)
                     VC2B_LANE_STEP(3, true)
@@ -452,6 +589,8 @@ __device__ __forceinline__ void lanes_block(const DevParams &P, const int comp, 
     }
     VC2B_LANE_CLOSE_BAND()
 #undef VC2B_LANE_STEP
+#undef VC2B_LANE_NEXT_BAND
+#undef VC2B_LANE_PAIR_VALUE
 #undef VC2B_LANE_SETTLE
 #undef VC2B_LANE_CLOSE_BAND
     if ((hiacc >> 1) != 0 || bad != 0) ovf = true;
@@ -460,6 +599,7 @@ __device__ __forceinline__ void lanes_block(const DevParams &P, const int comp, 
 __device__ __forceinline__ void build_lane_block(const DevParams &P, LaneBlock &S, int tid, int nthreads)
 {
     build_lane_lut(S.slut, tid, nthreads);
+    build_pair_lut(S.plut, tid, nthreads);
     build_qtab(S.qtab, tid, nthreads);
     for (int idx = tid; idx < 2 * kLaneBands; idx += nthreads) {
         const int mc = idx / kLaneBands, b = idx - mc * kLaneBands;
@@ -505,13 +645,14 @@ __device__ __forceinline__ void build_lane_block(const DevParams &P, LaneBlock &
 
 // One LANE per slice; a warp task is 32 consecutive slices of one picture.
 template <bool LD>
-__global__ void __launch_bounds__(kLaneWarps * 32, 6)
+__global__ void __launch_bounds__(kLaneWarps * 32, 2)
 unpack_lanes_kernel(DevParams P, const uint8_t *__restrict__ data, const int64_t *__restrict__ pic_offset,
                     int npictures, const uint32_t *__restrict__ slice_offset, int32_t *__restrict__ coeffs,
                     int32_t *__restrict__ qindex_out, int32_t *__restrict__ status)
 {
-    __shared__ LaneBlock S;
-    __shared__ LaneWarp Ws[kLaneWarps];
+    extern __shared__ __align__(16) uint8_t lane_smem[];
+    LaneBlock &S = *reinterpret_cast<LaneBlock *>(lane_smem);
+    LaneWarp *Ws = reinterpret_cast<LaneWarp *>(lane_smem + sizeof(LaneBlock));
     build_lane_block(P, S, threadIdx.x, blockDim.x);
 
     const int lane = threadIdx.x & 31;
@@ -590,6 +731,9 @@ unpack_lanes_kernel(DevParams P, const uint8_t *__restrict__ data, const int64_t
             atomicMax(&status[4 * pic + 3], (ovf || maxabs > 0x7fffffffu) ? 0x7fffffff : (int)maxabs);
     }
 }
+
+constexpr size_t kLaneSmemBytes = sizeof(LaneBlock) + kLaneWarps * sizeof(LaneWarp);
+static_assert(sizeof(LaneBlock) % 16 == 0, "LaneWarp array alignment");
 
 // Whether every slice component fits the lane-per-slice kernel.
 static bool lanes_eligible(const DevParams &P)
