@@ -62,6 +62,8 @@ typedef struct vc2b_params {
 #define VC2B_ST_UNEXPECTED_END_OF_STREAM 1 /* decoder/io.py:197 UnexpectedEndOfStream */
 #define VC2B_ST_INVALID_SLICE_Y_LENGTH 2   /* decoder/transform_data_syntax.py:166 */
 #define VC2B_ST_INT32_ENVELOPE 4           /* value outside the int32 envelope */
+#define VC2B_ST_COEFF16_RANGE 5            /* vc2b_unpack16 only: a high-pass coefficient does not fit int16;
+                                              decode this picture with vc2b_unpack + vc2b_idwt instead */
 
 /* ---- introspection --------------------------------------------------------------- */
 const char *vc2b_version(void);
@@ -117,6 +119,23 @@ int vc2b_unpack(const vc2b_params *p, const uint8_t *d_data, const int64_t *d_pi
                 int npictures, const uint32_t *d_slice_offset, int32_t *d_coeffs,
                 int32_t *d_qindex, int32_t *d_status, void *stream);
 
+/* The same call with the INT16 COEFFICIENT PLANE: inverse-quantised coefficients of every subband but the
+ * level-0 band are stored as int16 in d_coeffs16 (same element offsets as d_coeffs; only the level-0 band
+ * -- which dc_prediction and the first synthesis level read as int32 -- is written to d_coeffs).  Halves the
+ * bytes the coefficients cost on their way through HBM (the path is bandwidth-bound: DESIGN.md 5).  Values are
+ * the same integers; a picture with a high-pass coefficient outside int16 gets VC2B_ST_COEFF16_RANGE and must
+ * be decoded again through vc2b_unpack (device.BatchCodec does).  Needs vc2b_coeff16_supported(p). */
+int vc2b_unpack16(const vc2b_params *p, const uint8_t *d_data, const int64_t *d_pic_offset,
+                  int npictures, const uint32_t *d_slice_offset, int32_t *d_coeffs, int16_t *d_coeffs16,
+                  int32_t *d_qindex, int32_t *d_status, void *stream);
+/* 1 if the int16 coefficient plane is available for this parameter set: lane-per-slice unpack geometry and
+ * every transform level on the wide synthesis kernel (2-D levels only, one filter, vector-aligned bands). */
+int vc2b_coeff16_supported(const vc2b_params *p);
+/* Test hook: which slice-unpack kernel vc2b_unpack uses.  0 = chosen by geometry (default), 1 = warp per
+ * slice, 2 = lane per slice (VC2B_E_UNSUPPORTED from vc2b_unpack if the geometry does not allow it).
+ * Process-wide; the GPU tests run both kernels on the same streams. */
+int vc2b_set_unpack_kernel(int kernel);
+
 /* dc_prediction (decoder/transform_data_syntax.py:63) of the level-0 band of every component,
  * in place.  vc2b_unpack already applies it for LD; exposed for the function-level API. */
 int vc2b_dc_prediction(const vc2b_params *p, int32_t *d_coeffs, int npictures, int inverse,
@@ -131,6 +150,9 @@ int vc2b_dc_prediction(const vc2b_params *p, int32_t *d_coeffs, int npictures, i
  *               in flight per launch */
 int vc2b_idwt(const vc2b_params *p, const int32_t *d_coeffs, int npictures, uint16_t *d_pictures,
               void *d_scratch, int64_t scratch_bytes, void *stream);
+/* picture_decode from the int16 coefficient plane of vc2b_unpack16 (d_coeffs supplies the level-0 bands). */
+int vc2b_idwt16(const vc2b_params *p, const int32_t *d_coeffs, const int16_t *d_coeffs16, int npictures,
+                uint16_t *d_pictures, void *d_scratch, int64_t scratch_bytes, void *stream);
 /* idwt (:88) alone for ONE component: no crop, clip or offset; int32 out, padded dimensions. */
 int vc2b_idwt_raw(const vc2b_params *p, int comp, const int32_t *d_coeffs, int32_t *d_out,
                   void *d_scratch, int64_t scratch_bytes, void *stream);

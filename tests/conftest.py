@@ -38,18 +38,18 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
-@pytest.fixture(params=["auto", "warp"])
+@pytest.fixture(params=["auto", "warp", "coeff16"])
 def unpack_kernel(request):
     """Runs a test once with the library's own choice of unpack kernel (lane-per-slice where the
-    slices are small) and once with the warp-per-slice kernel forced (VC2B_UNPACK, read by
-    vc2b_unpack at every call)."""
-    old = os.environ.get("VC2B_UNPACK")
-    if request.param == "auto":
-        os.environ.pop("VC2B_UNPACK", None)
-    else:
-        os.environ["VC2B_UNPACK"] = request.param
+    slices are small), once with the warp-per-slice kernel forced (vc2b_set_unpack_kernel) and once with
+    BatchCodec decoding through the int16 coefficient plane (vc2b_unpack16 / vc2b_idwt16, with its
+    fall-back to the int32 plane for pictures that do not fit)."""
+    from vc2_conformance_b200 import capi, device
+
+    L = capi.lib()
+    old16 = device.DEFAULT_COEFF16
+    L.vc2b_set_unpack_kernel(1 if request.param == "warp" else 0)
+    device.DEFAULT_COEFF16 = request.param == "coeff16"
     yield request.param
-    if old is None:
-        os.environ.pop("VC2B_UNPACK", None)
-    else:
-        os.environ["VC2B_UNPACK"] = old
+    L.vc2b_set_unpack_kernel(0)
+    device.DEFAULT_COEFF16 = old16

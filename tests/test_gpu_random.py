@@ -269,72 +269,89 @@ def test_full_size_ld_field():
     assert out[0] == streams[0] and out[1] == streams[1]
 
 
-@pytest.mark.parametrize("case", [HQ_CASES[0], HQ_CASES[2], HQ_CASES[4]])
-def test_idwt_l2_subgroups(case, monkeypatch):
-    """The last two IDWT levels run over L2-sized sub-groups of pictures through shared scratch slots
-    (idwt.cu run_idwt); every sub-group size and hint mode must give the oracle's pictures."""
-    from vc2_conformance_b200.device import BatchCodec
-
-    import oracle as O
-
-    W, H, cw, ch, depth, wi, wiho, d, dho, sx, sy, scaler = case
-    S = W * H + 2 * cw * ch
-    scaler = max(scaler, O.safe_lossy_hq_slice_size_scaler(2 * S, sx * sy))
-    p = _mk(luma_width=W, luma_height=H, color_diff_width=cw, color_diff_height=ch, luma_depth=depth,
-            wavelet_index=wi, wavelet_index_ho=wiho, dwt_depth=d, dwt_depth_ho=dho, slices_x=sx, slices_y=sy,
-            slice_size_scaler=scaler)
-    pics = [synth.noise_picture(p, 20 + i) if i % 2 == 0 else synth.ramp_picture(p, 20 + i) for i in range(7)]
-    streams, decoded = _oracle_streams(p, pics, [S // 2] * len(pics))
-    monkeypatch.setenv("VC2B_IDWT_FUSED", "0")  # the fused pair of levels bypasses the per-level launches
-    for group, hints in [("0", "0"), ("1", "1"), ("2", "3"), ("3", "2"), ("5", "1")]:
-        monkeypatch.setenv("VC2B_IDWT_L2_GROUP", group)
-        monkeypatch.setenv("VC2B_IDWT_L2_HINTS", hints)
-        codec = BatchCodec(p, len(pics))
-        codec.pictures.view(codec.torch.int16).fill_(-1)
-        codec.decode_streams(streams)
-        for i in range(len(pics)):
-            planes = codec.picture_planes(i)
-            for c in range(3):
-                assert (planes[c] == decoded[i][c]).all(), (case, group, hints, i, c)
-
-
-FUSED_CASES = [
-    # W, H, cw, ch, depth, wavelet, dwt_depth: several tiles across and down, ragged right / bottom edges,
-    # pictures narrower than one tile, padded dimensions
-    (1920, 1080, 960, 1080, 10, 0, 3),
-    (1000, 600, 500, 600, 10, 0, 2),
-    (1000, 600, 500, 300, 12, 1, 3),
-    (3840, 272, 1920, 272, 10, 0, 4),
-    (480, 1000, 480, 1000, 8, 1, 2),
-    (456, 130, 232, 66, 10, 0, 2),
+COEFF16_CASES = [
+    # W, H, cw, ch, depth, wavelet, dwt_depth, slices_x, slices_y, int16 plane expected
+    (1920, 1080, 960, 1080, 10, 0, 3, 60, 135, True),    # several strips across and down
+    (1000, 600, 500, 600, 10, 0, 2, 25, 75, False),      # level-1 bands 250 wide: not vector aligned
+    (1056, 600, 528, 600, 10, 0, 2, 33, 75, True),       # ragged right / bottom strips
+    (1000, 600, 500, 300, 12, 1, 3, 25, 75, False),      # chroma bands 63 wide: not vector aligned
+    (3840, 272, 1920, 272, 10, 0, 4, 120, 17, True),     # the bench geometry (32 x 16 slices), padded height
+    (480, 1000, 480, 1000, 8, 1, 2, 15, 125, True),      # LeGall
+    (512, 256, 256, 256, 10, 2, 2, 16, 32, True),        # Deslauriers-Dubuc (13,7)
+    (512, 256, 256, 256, 10, 4, 3, 16, 32, True),        # Haar with shift
+    (512, 256, 256, 256, 10, 6, 2, 16, 32, True),        # Daubechies (9,7)
+    (456, 130, 232, 66, 10, 0, 2, 19, 11, False),        # uneven slices, padded dimensions
+    (640, 480, 320, 480, 10, 0, 2, 4, 2, False),         # large slices: warp-per-slice unpack, int32 plane
 ]
 
 
-@pytest.mark.parametrize("case", FUSED_CASES)
-def test_idwt_fused_levels(case, monkeypatch):
-    """The last two levels run in one kernel (idwt_fused2_kernel) where the filter allows it; the result
-    must equal the oracle and the one-launch-per-level path."""
+@pytest.mark.parametrize("case", COEFF16_CASES)
+@pytest.mark.parametrize("group", [128, 2])
+def test_coeff16_plane(case, group):
+    """vc2b_unpack16 + vc2b_idwt16 (high-pass coefficients staged as int16) give the oracle's coefficients and
+    pictures; parameter sets the plane does not support quietly use the int32 plane."""
     import oracle as O
     from vc2_conformance_b200.device import BatchCodec
 
-    W, H, cw, ch, depth, wi, d = case
-    sx, sy = 4, 2
+    W, H, cw, ch, depth, wi, d, sx, sy, expect16 = case
     S = W * H + 2 * cw * ch
     p = _mk(luma_width=W, luma_height=H, color_diff_width=cw, color_diff_height=ch, luma_depth=depth,
             wavelet_index=wi, dwt_depth=d, slices_x=sx, slices_y=sy,
             slice_size_scaler=O.safe_lossy_hq_slice_size_scaler(2 * S, sx * sy))
+    po = synth.oracle_params(p)
     pics = [synth.noise_picture(p, 40), synth.ramp_picture(p, 41), synth.noise_picture(p, 42)]
     streams, decoded = _oracle_streams(p, pics, [S, S // 2, S // 3])
-    outs = []
-    for fused in ("1", "0"):  # opt-in fused pair, then the default per-level launches
-        monkeypatch.setenv("VC2B_IDWT_FUSED", fused)
-        codec = BatchCodec(p, len(pics))
-        codec.pictures.view(codec.torch.int16).fill_(-1)
-        codec.decode_streams(streams)
-        for i in range(len(pics)):
-            planes = codec.picture_planes(i)
-            for c in range(3):
-                assert (planes[c] == decoded[i][c]).all(), (case, fused, i, c)
+    codec = BatchCodec(p, len(pics), group=group, coeff16=True)
+    assert codec.coeff16 == expect16
+    codec.pictures.view(codec.torch.int16).fill_(-1)
+    codec.decode_streams(streams)
+    for i in range(len(pics)):
+        st, comps, _q, _c = O.transform_data(po, streams[i])[:4]
+        got = codec.coeff_components(i)
+        planes = codec.picture_planes(i)
+        for c in range(3):
+            assert (got[c] == np.asarray(comps[c]).reshape(-1)).all(), (case, "coefficients", i, c)
+            assert (planes[c] == decoded[i][c]).all(), (case, "picture", i, c)
+
+
+def test_coeff16_overflow_is_redone_through_the_int32_plane():
+    """A lossless 16-bit noise picture has high-pass coefficients beyond int16: the int16 plane reports
+    VC2B_ST_COEFF16_RANGE for it, and decode_streams / SequenceDecoder.finish decode it again through the
+    int32 plane; pictures that fit (the ramp) are left alone."""
+    from vc2_conformance_b200 import capi
+    from vc2_conformance_b200.device import BatchCodec, SequenceDecoder
+
+    W, H = 512, 256
+    p = _mk(luma_width=W, luma_height=H, color_diff_width=W // 2, color_diff_height=H, luma_depth=16,
+            wavelet_index=0, dwt_depth=3, slices_x=16, slices_y=32, slice_size_scaler=8)
+    pics = [synth.noise_picture(p, 50), synth.ramp_picture(p, 51), synth.noise_picture(p, 52),
+            synth.ramp_picture(p, 53)]
+    streams, decoded = _oracle_streams(p, pics, [None] * len(pics))
+    codec = BatchCodec(p, len(pics), coeff16=True)
+    assert codec.coeff16
+    host, offs = codec.pack_host_streams(streams)
+    codec.decode_host(host, offs, len(pics))
+    st = codec.status_host(len(pics))
+    assert list(st[:, 0]) == [capi.ST_COEFF16_RANGE, capi.ST_OK, capi.ST_COEFF16_RANGE, capi.ST_OK]
+    assert codec.redo_coeff16(st) == [0, 2]
+    assert (st[:, 0] == capi.ST_OK).all()
+    for i in range(len(pics)):
+        planes = codec.picture_planes(i)
+        for c in range(3):
+            assert (planes[c] == decoded[i][c]).all(), (i, c)
+
+    # the pipelined host-to-host decoder
+    torch = codec.torch
+    seq = SequenceDecoder(p, chunk=3, nstreams=2, max_chunk_bytes=sum(len(s) for s in streams) + 256)
+    chunks = seq.plan(host, offs.numpy())
+    out = torch.empty((len(pics), codec.g.picture_samples), dtype=torch.uint16).pin_memory()
+    seq.decode(chunks, out)
+    seq.synchronize()
+    st = seq.finish(chunks, out)
+    assert (st[:, 0] == capi.ST_OK).all()
+    flat = out.numpy()
+    for i in range(len(pics)):
+        assert (flat[i] == synth.flat_picture(decoded[i])).all(), i
 
 
 @pytest.mark.parametrize("mag_bits", [12, 27, 28, 29, 30])

@@ -13,10 +13,11 @@ ap.add_argument("--workload", default="cfg2")
 ap.add_argument("--pictures", type=int, default=16)
 ap.add_argument("--group", type=int, default=128)
 ap.add_argument("--iters", type=int, default=10)
+ap.add_argument("--int32-plane", action="store_true")
 a = ap.parse_args()
 w = bench.make_workload(a.workload, a.pictures)
 p, NP, S = w["p"], w["pictures"], w["samples"]
-codec = BatchCodec(p, NP, max_stream_bytes=NP * (w["picture_bytes"] + 64), group=a.group)
+codec = BatchCodec(p, NP, max_stream_bytes=NP * (w["picture_bytes"] + 64), group=a.group, coeff16=not a.int32_plane)
 pics = bench.synth_pictures(w, 0, 0, min(NP, 4))
 streams = codec.encode_pictures(pics, w["picture_bytes"])
 streams = [streams[i % len(streams)] for i in range(NP)]
@@ -33,9 +34,7 @@ def run_idwt():
 def run_dwt():
     codec.dwt_device(NP)
 def run_unpack():
-    if not p.is_ld:
-        L.vc2b_hq_slice_offsets(C.byref(p), _ptr(codec.data), _ptr(codec.pic_offset), NP, _ptr(codec.slice_offset), _ptr(codec.status), sp)
-    L.vc2b_unpack(C.byref(p), _ptr(codec.data), _ptr(codec.pic_offset), NP, _ptr(codec.slice_offset), _ptr(codec.coeffs), _ptr(codec.qindex), _ptr(codec.status), sp)
+    codec.unpack_device(codec.data, codec.pic_offset, NP)
 def run_walk():
     L.vc2b_hq_slice_offsets(C.byref(p), _ptr(codec.data), _ptr(codec.pic_offset), NP, _ptr(codec.slice_offset), _ptr(codec.status), sp)
 def run_dc():      # apply_dc_prediction then dc_prediction: the band returns to its values, so iterations are alike
@@ -62,5 +61,5 @@ for _ in range(a.iters):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / a.iters
-print("%s %s: %.3f ms per %d pictures = %.1f us/picture, %.1f GB/s algorithmic (%.1f%% of 6542)" % (
-    a.stage, a.workload, ms, NP, 1000 * ms / NP, nbytes / ms / 1e6, 100 * nbytes / ms / 1e6 / 6542.4))
+print("[plane %s] %s %s: %.3f ms per %d pictures = %.1f us/picture, %.1f GB/s algorithmic (%.1f%% of 6542)" % (
+    "int16" if codec.coeff16 else "int32", a.stage, a.workload, ms, NP, 1000 * ms / NP, nbytes / ms / 1e6, 100 * nbytes / ms / 1e6 / 6542.4))

@@ -21,6 +21,7 @@ ST_OK = 0
 ST_UNEXPECTED_END_OF_STREAM = 1
 ST_INVALID_SLICE_Y_LENGTH = 2
 ST_INT32_ENVELOPE = 4
+ST_COEFF16_RANGE = 5
 
 
 class Params(C.Structure):
@@ -113,8 +114,12 @@ SIGNATURES = {
     "vc2b_idwt_max_safe_coeff": (_i64, [_PP]),
     "vc2b_hq_slice_offsets": (_i, [_PP, _vp, _vp, _i, _vp, _vp, _vp]),
     "vc2b_unpack": (_i, [_PP, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "vc2b_unpack16": (_i, [_PP, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vc2b_coeff16_supported": (_i, [_PP]),
+    "vc2b_set_unpack_kernel": (_i, [_i]),
     "vc2b_dc_prediction": (_i, [_PP, _vp, _i, _i, _vp]),
     "vc2b_idwt": (_i, [_PP, _vp, _i, _vp, _vp, _i64, _vp]),
+    "vc2b_idwt16": (_i, [_PP, _vp, _vp, _i, _vp, _vp, _i64, _vp]),
     "vc2b_idwt_raw": (_i, [_PP, _i, _vp, _vp, _vp, _i64, _vp]),
     "vc2b_dwt": (_i, [_PP, _vp, _i, _vp, _vp, _i64, _vp]),
     "vc2b_dwt_raw": (_i, [_PP, _i, _vp, _vp, _vp, _i64, _vp]),

@@ -48,6 +48,8 @@ struct DevParams {
 int make_dev_params(const vc2b_params *p, DevParams *d);
 // Largest |coefficient| for which the int32 synthesis provably cannot overflow (params.cu).
 long long idwt_max_safe_coeff(const vc2b_params *p);
+// Whether vc2b_unpack16 (lane-per-slice kernel, int16 coefficient plane) supports this parameter set (unpack.cu).
+bool lanes_unpack_ok(const DevParams &P);
 // Whether the int32 analysis of samples of the given depth provably cannot overflow.
 bool dwt_is_safe(const vc2b_params *p);
 

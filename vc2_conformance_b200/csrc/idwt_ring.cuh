@@ -229,8 +229,6 @@ idwt_ring_kernel(LevelArgs A)
     X.ld_hints = false;
     X.pol_ll = X.pol_hb = 0;
     X.pol_out = l2_policy(A.hint_out);
-    X.ring = nullptr;
-    X.ring_q = 0;
 
     const int last = X.h - 1;
     const int K0 = ty * C::RSP, K1 = min(K0 + C::RSP, X.h);

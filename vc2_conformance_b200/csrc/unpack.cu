@@ -230,8 +230,12 @@ __global__ void finalize_status_kernel(int npictures, int32_t *__restrict__ stat
     int key = status[4 * pic + 0];
     if (key == kErrOk) {
         // a value left the int32 envelope (the reference, in unbounded integers, would carry on):
-        // reported only when the stream has no error the reference itself would raise
-        status[4 * pic + 0] = (status[4 * pic + 3] > max_safe_coeff) ? VC2B_ST_INT32_ENVELOPE : VC2B_ST_OK;
+        // reported only when the stream has no error the reference itself would raise.  Word 1 is the
+        // int16-plane overflow flag of unpack_lanes_kernel<.., C16>.
+        // (an int16-plane overflow comes first: decoding the picture again through the int32 plane then stores
+        // every value exactly and reports the int32 envelope itself)
+        status[4 * pic + 0] = status[4 * pic + 1] != 0 ? VC2B_ST_COEFF16_RANGE
+                              : (status[4 * pic + 3] > max_safe_coeff ? VC2B_ST_INT32_ENVELOPE : VC2B_ST_OK);
         status[4 * pic + 1] = -1;
     } else {
         status[4 * pic + 0] = key & 7;
@@ -1018,6 +1022,12 @@ static int launch_dc_fwd(const DevParams &P, int32_t *d_coeffs, int npictures, i
 
 }  // namespace vc2b
 
+namespace vc2b {
+bool lanes_unpack_ok(const DevParams &P) { return lanes16_eligible(P); }
+// vc2b_set_unpack_kernel: 0 = by geometry, 1 = warp per slice, 2 = lane per slice
+static int g_unpack_kernel = 0;
+}  // namespace vc2b
+
 using namespace vc2b;
 
 extern "C" {
@@ -1050,9 +1060,10 @@ int vc2b_dc_prediction(const vc2b_params *p, int32_t *d_coeffs, int npictures, i
     return 0;
 }
 
-int vc2b_unpack(const vc2b_params *p, const uint8_t *d_data, const int64_t *d_pic_offset, int npictures,
-                const uint32_t *d_slice_offset, int32_t *d_coeffs, int32_t *d_qindex, int32_t *d_status,
-                void *stream)
+// vc2b_unpack and vc2b_unpack16 (d_coeffs16 != nullptr: the int16 coefficient plane)
+static int unpack_impl(const vc2b_params *p, const uint8_t *d_data, const int64_t *d_pic_offset, int npictures,
+                       const uint32_t *d_slice_offset, int32_t *d_coeffs, int16_t *d_coeffs16, int32_t *d_qindex,
+                       int32_t *d_status, void *stream)
 {
     DevParams P;
     int st = make_dev_params(p, &P);
@@ -1061,12 +1072,12 @@ int vc2b_unpack(const vc2b_params *p, const uint8_t *d_data, const int64_t *d_pi
     cudaStream_t s = (cudaStream_t)stream;
     if (!P.is_ld && !d_slice_offset) return VC2B_E_BAD_PARAMS;
     // Small slices (the production geometry): one LANE per slice.  Large slices: one WARP per slice.
-    // VC2B_UNPACK=warp|lanes overrides the choice (tests exercise both kernels on the same streams).
+    // vc2b_set_unpack_kernel overrides the choice (tests exercise both kernels on the same streams).
     bool lanes = lanes_eligible(P);
-    if (const char *force = getenv("VC2B_UNPACK")) {
-        if (!strcmp(force, "warp")) lanes = false;
-        if (!strcmp(force, "lanes") && !lanes) return VC2B_E_UNSUPPORTED;
-    }
+    const int forced = g_unpack_kernel;
+    if (forced == 1) lanes = false;
+    if (forced == 2 && !lanes) return VC2B_E_UNSUPPORTED;
+    if (d_coeffs16 && !(lanes && lanes16_eligible(P))) return VC2B_E_UNSUPPORTED;
     if (P.is_ld) {
         ld_init_status_kernel<<<(npictures + 127) / 128, 128, 0, s>>>(P, d_pic_offset, npictures, d_status);
         VC2B_CHECK_LAUNCH();
@@ -1074,21 +1085,20 @@ int vc2b_unpack(const vc2b_params *p, const uint8_t *d_data, const int64_t *d_pi
     if (lanes) {
         const long long tasks = (long long)npictures * ((P.slices_x * P.slices_y + 31) / 32);
         long long nblk = (tasks + kLaneWarps - 1) / kLaneWarps;
-        // persistent: two CTAs of twelve warps per SM (the two-code table is 32 KB per CTA)
+        // persistent: two CTAs of twelve warps per SM (the two-code table is 16 KB per CTA)
         const long long max_blocks = 148LL * 2;
         if (nblk > max_blocks) nblk = max_blocks;
+        const void *fn = P.is_ld ? (d_coeffs16 ? (const void *)unpack_lanes_kernel<true, true>
+                                               : (const void *)unpack_lanes_kernel<true, false>)
+                                 : (d_coeffs16 ? (const void *)unpack_lanes_kernel<false, true>
+                                               : (const void *)unpack_lanes_kernel<false, false>);
         // the attribute is per device: set at every launch (a process may drive several GPUs)
-        if (P.is_ld) {
-            cudaFuncSetAttribute(unpack_lanes_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)kLaneSmemBytes);
-            unpack_lanes_kernel<true><<<(unsigned)nblk, kLaneWarps * 32, kLaneSmemBytes, s>>>(
-                P, d_data, d_pic_offset, npictures, nullptr, d_coeffs, d_qindex, d_status);
-        } else {
-            cudaFuncSetAttribute(unpack_lanes_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)kLaneSmemBytes);
-            unpack_lanes_kernel<false><<<(unsigned)nblk, kLaneWarps * 32, kLaneSmemBytes, s>>>(
-                P, d_data, d_pic_offset, npictures, d_slice_offset, d_coeffs, d_qindex, d_status);
-        }
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLaneSmemBytes);
+        if (e != cudaSuccess) return (int)e;
+        const uint32_t *so = P.is_ld ? nullptr : d_slice_offset;
+        void *args[] = {&P, &d_data, &d_pic_offset, &npictures, &so, &d_coeffs, &d_coeffs16, &d_qindex, &d_status};
+        e = cudaLaunchKernel(fn, dim3((unsigned)nblk), dim3(kLaneWarps * 32), args, kLaneSmemBytes, s);
+        if (e != cudaSuccess) return (int)e;
         VC2B_CHECK_LAUNCH();
     } else {
         const long long warps = (long long)npictures * P.slices_x * P.slices_y;
@@ -1115,6 +1125,30 @@ int vc2b_unpack(const vc2b_params *p, const uint8_t *d_data, const int64_t *d_pi
     if (safe > 0x7ffffffeLL) safe = 0x7ffffffeLL;  // 0x7fffffff marks a value that did not fit int32
     finalize_status_kernel<<<(npictures + 127) / 128, 128, 0, s>>>(npictures, d_status, (int)safe);
     VC2B_CHECK_LAUNCH();
+    return 0;
+}
+
+int vc2b_unpack(const vc2b_params *p, const uint8_t *d_data, const int64_t *d_pic_offset, int npictures,
+                const uint32_t *d_slice_offset, int32_t *d_coeffs, int32_t *d_qindex, int32_t *d_status,
+                void *stream)
+{
+    return unpack_impl(p, d_data, d_pic_offset, npictures, d_slice_offset, d_coeffs, nullptr, d_qindex, d_status,
+                       stream);
+}
+
+int vc2b_unpack16(const vc2b_params *p, const uint8_t *d_data, const int64_t *d_pic_offset, int npictures,
+                  const uint32_t *d_slice_offset, int32_t *d_coeffs, int16_t *d_coeffs16, int32_t *d_qindex,
+                  int32_t *d_status, void *stream)
+{
+    if (!d_coeffs16) return VC2B_E_BAD_PARAMS;
+    return unpack_impl(p, d_data, d_pic_offset, npictures, d_slice_offset, d_coeffs, d_coeffs16, d_qindex, d_status,
+                       stream);
+}
+
+int vc2b_set_unpack_kernel(int kernel)
+{
+    if (kernel < 0 || kernel > 2) return VC2B_E_BAD_PARAMS;
+    g_unpack_kernel = kernel;
     return 0;
 }
 

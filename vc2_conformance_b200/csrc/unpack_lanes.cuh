@@ -45,7 +45,9 @@ struct __align__(16) LaneBlock {                       // per-CTA shared memory
     int32_t even_x[2][kLaneBands];       // ref_w if the band divides evenly between the slices, else -1
     int32_t even_y[2][kLaneBands];
     int32_t ref_cnt[2][kLaneBands];      // ref_w * ref_h
+    int32_t even16[2][kLaneBands];       // 1: every rectangle of the band starts at an even element offset
     int32_t ref_ncoef[2];
+    int32_t pad_[2];
     uint32_t slut[256];                  // 8-bit window -> 2^length | magnitude << 16 | sign << 30 (0: longer code)
     uint2 qtab[kQTab];
     uint32_t plut[kPairEntries];         // 12-bit window -> the next TWO codes (build_pair_lut)
@@ -593,7 +595,232 @@ __device__ __forceinline__ void lanes_block(const DevParams &P, const int comp, 
 #undef VC2B_LANE_PAIR_VALUE
 #undef VC2B_LANE_SETTLE
 #undef VC2B_LANE_CLOSE_BAND
-    if ((hiacc >> 1) != 0 || bad != 0) ovf = true;
+    if ((hiacc >> 1) != 0 || (bad & 3u) != 0) ovf = true;
+}
+
+// ---- the int16 coefficient plane (vc2b_unpack16) -----------------------------------------------------
+// Same decoding as lanes_block for parameter sets whose slices all have the reference rectangles
+// (lanes16_eligible).  Every band but the level-0 band is stored as int16 in `o16` / `o16b` at the element
+// offsets of the int32 layout, which halves what the coefficients cost on their way to the IDWT (the largest
+// DRAM stream of the decoder) and the shared-memory and store traffic of this kernel: the tile holds TWO codes
+// per 32-bit word, a chunk is 32 codes, and a store instruction writes 32 consecutive coefficients of two
+// slices (one 32-bit store per lane where a pair of codes is adjacent in its band, which is everywhere but in
+// the smallest bands).  The level-0 band -- a couple of values per slice that DC prediction and the first
+// synthesis level read as int32 -- goes straight from the decoding lane to the int32 plane.  A high-pass value
+// outside int16 sets `ovf16`; the picture is then decoded again through the int32 plane.
+template <bool INTERLEAVED>
+__device__ __forceinline__ void lanes_block16(const DevParams &P, const int comp, LaneWarp &W, const LaneBlock &S,
+                                              const bool active, const int sx, const int sy, const int qindex,
+                                              const uint8_t *blk, const int bit_off, const long long nbits,
+                                              int32_t *__restrict__ out, int32_t *__restrict__ out2,
+                                              int16_t *__restrict__ o16, int16_t *__restrict__ o16b, const int lane,
+                                              uint32_t &maxabs, bool &ovf, bool &ovf16)
+{
+    constexpr int I = INTERLEAVED ? 1 : 0;
+    constexpr int CH = 32;             // codes per chunk
+    constexpr int TS2 = 2 * kLaneTS;   // int16 elements per tile row
+    const int mc = comp ? 1 : 0;
+    const int nb = P.nb;
+
+    __syncwarp();
+    for (int b = 0; b < nb; b++) {
+        const Band &B = P.band[comp][b];
+        W.base[lane * kLaneBaseStride + b] = active ? B.off + (S.ref_h[mc][b] * sy) * B.w + S.ref_w[mc][b] * sx : 0;
+    }
+    const int ncodes = min(S.ref_ncoef[mc], kLaneMaxCoef) << I;
+    const uint32_t act_mask = __ballot_sync(0xffffffffu, active);
+    __syncwarp();
+    if (act_mask == 0) return;
+
+    LaneReader R;
+    lane_reader_init(R, (uint32_t)__cvta_generic_to_shared(&W.stage[0][lane]), blk, bit_off, nbits, active);
+
+    int b = -1, next = 0;
+    uint32_t qf = 0, qo = 0, maxmag = 0;
+    uint32_t slut_addr = (uint32_t)__cvta_generic_to_shared(S.slut);
+    asm volatile("" : "+r"(slut_addr));
+    uint32_t plut_addr = (uint32_t)__cvta_generic_to_shared(S.plut);
+    asm volatile("" : "+r"(plut_addr));
+    int16_t *t16 = reinterpret_cast<int16_t *>(&W.tile[lane]);
+    const int base0 = W.base[lane * kLaneBaseStride];
+    uint32_t hiacc = 0, bad = 0, mark = 1;
+    bool qfast = false;
+
+#define VC2B_LANE_CLOSE_BAND()                                                                       \
+    if (maxmag) {                                                                                    \
+        const unsigned long long tm = (unsigned long long)maxmag * qf + qo;                          \
+        maxabs = max(maxabs, (uint32_t)(tm >> 2));                                                   \
+        hiacc |= (uint32_t)(tm >> 32);                                                               \
+        if (qf == 0xffffffffu) bad |= 2u;                                                            \
+        if (b > 0 && (tm >> 2) > 32767ull) bad |= 4u;                                                \
+        maxmag = 0;                                                                                  \
+    }
+
+#define VC2B_LANE_SETTLE()                                                                           \
+    {                                                                                                \
+        R.avail -= mark ? 31 - __clz(mark) : 32;                                                     \
+        mark = 1;                                                                                    \
+    }
+
+    // the band of code j0 + i starts here; the level-0 band never takes the two-code path (its values are
+    // stored by VC2B_LANE_STEP16 as int32)
+#define VC2B_LANE_NEXT_BAND(i)                                                                       \
+    {                                                                                                \
+        VC2B_LANE_CLOSE_BAND()                                                                       \
+        do {                                                                                         \
+            b++;                                                                                     \
+            next += S.ref_cnt[mc][b] << I;                                                           \
+        } while (j0 + (i) == next);                                                                  \
+        const int q = max(qindex - P.band[comp][b].qm, 0);                                           \
+        const uint2 qq = S.qtab[min(q, kQTab - 1)];                                                  \
+        qf = qq.x;                                                                                   \
+        qo = qq.y;                                                                                   \
+        qfast = qf <= kPairMaxQf && b > 0;                                                           \
+    }
+
+    // one code: read_sintb + inverse_quant; value to half (i & 1) of tile row i >> 1
+#define VC2B_LANE_STEP16(i, CHK)                                                                     \
+    {                                                                                                \
+        if (CHK && j0 + (i) == next) VC2B_LANE_NEXT_BAND(i)                                          \
+        const uint32_t hi = (uint32_t)(R.buf >> 32);                                                 \
+        const uint32_t e = lds_u32(slut_addr + 4 * (hi >> 24));                                      \
+        const uint32_t M = e & 0x1ffu;                                                               \
+        uint32_t mag = __byte_perm(e, 0, 0x4442);                                                    \
+        int sgn = __mulhi((int)e, 4);                                                                \
+        if (__builtin_expect(M == 0, 0)) {                                                           \
+            VC2B_LANE_SETTLE()                                                                       \
+            const LaneLong o = lane_read_long_cold(R);                                               \
+            R = o.R;                                                                                 \
+            mag = o.mag;                                                                             \
+            sgn = o.neg ? -1 : 1;                                                                    \
+            if (!o.ok) {                                                                             \
+                bad |= 1u;                                                                           \
+                lane_reader_kill(R);                                                                 \
+            }                                                                                        \
+        } else {                                                                                     \
+            R.buf *= M;                                                                              \
+            mark *= M;                                                                               \
+        }                                                                                            \
+        const uint32_t t = (uint32_t)(((unsigned long long)mag * qf + qo) >> 2);                     \
+        maxmag = max(maxmag, mag);                                                                   \
+        const int32_t val = (int32_t)t * sgn;                                                        \
+        if (b == 0) {                                                                                \
+            if (active) {                                                                            \
+                int32_t *d32 = (INTERLEAVED && ((j0 + (i)) & 1)) ? out2 : out;                       \
+                d32[base0 + (int)(S.map[mc][(j0 + (i)) >> I] & 0x3ffffffu)] = val;                   \
+            }                                                                                        \
+        } else {                                                                                     \
+            t16[((i) >> 1) * TS2 + ((i) & 1)] = (int16_t)val;                                        \
+        }                                                                                            \
+    }
+
+#define VC2B_LANE_PAIR16(i, m1, s1, m2, s2)                                                          \
+    {                                                                                                \
+        const int32_t v1 = (int32_t)(((m1) * qf + qo) >> 2) * (s1);                                  \
+        const int32_t v2 = (int32_t)(((m2) * qf + qo) >> 2) * (s2);                                  \
+        reinterpret_cast<uint32_t *>(t16)[(i) * kLaneTS] = __byte_perm((uint32_t)v1, (uint32_t)v2, 0x5410); \
+    }
+
+    const int c = lane & 15, h = lane >> 4;   // store phase: half-warp h takes slice 2k+h, lane c its pair c
+    for (int j0 = 0; j0 < ncodes; j0 += CH) {
+        // ---- decode: lane = slice, CH codes each ---------------------------------------------------
+        if (j0 + CH <= ncodes) {
+#pragma unroll 1
+            for (int g = 0; g < CH / 4; g++) {
+                if (j0 == next) VC2B_LANE_NEXT_BAND(0)
+                if (next - j0 >= 4) {
+                    const uint32_t ea = lds_u32(plut_addr + (((uint32_t)(R.buf >> 32) >> (32 - kPairBits)) << 2));
+                    const uint32_t la = ea & 15u;
+                    const uint64_t bufa = R.buf << la;
+                    const uint32_t eb = lds_u32(plut_addr + (((uint32_t)(bufa >> 32) >> (32 - kPairBits)) << 2));
+                    const uint32_t lb = eb & 15u;
+                    if (__all_sync(0xffffffffu, qfast && la * lb != 0)) {
+                        R.buf = bufa << lb;
+                        R.avail -= (int)(la + lb);
+                        const uint32_t ma1 = __byte_perm(ea, 0, 0x4441), ma2 = __byte_perm(ea, 0, 0x4442);
+                        const uint32_t mb1 = __byte_perm(eb, 0, 0x4441), mb2 = __byte_perm(eb, 0, 0x4442);
+                        VC2B_LANE_PAIR16(0, ma1, __mulhi((int)ea, 4), ma2, __mulhi((int)(ea << 24), 4))
+                        VC2B_LANE_PAIR16(1, mb1, __mulhi((int)eb, 4), mb2, __mulhi((int)(eb << 24), 4))
+                        maxmag = max(max(maxmag, max(ma1, ma2)), max(mb1, mb2));
+                    } else {
+                        VC2B_LANE_STEP16(0, false)
+                        VC2B_LANE_STEP16(1, false)
+                        VC2B_LANE_STEP16(2, false)
+                        VC2B_LANE_STEP16(3, false)
+                    }
+                } else {
+                    VC2B_LANE_STEP16(0, false)
+                    VC2B_LANE_STEP16(1, true)
+                    VC2B_LANE_STEP16(2, true)
+                    VC2B_LANE_STEP16(3, true)
+                }
+                VC2B_LANE_SETTLE()
+                lane_refill(R);
+                j0 += 4;
+                t16 += 2 * TS2;
+            }
+            j0 -= CH;
+            t16 -= (CH / 2) * TS2;
+        } else {
+#pragma unroll 1
+            for (int i = 0; i < CH; i++) {
+                if (j0 < ncodes) VC2B_LANE_STEP16(0, true)
+                VC2B_LANE_SETTLE()
+                if (R.avail < 32) lane_refill(R);
+                j0 += 1;
+                t16 += (i & 1) ? TS2 - 1 : 1;
+            }
+            j0 -= CH;
+            t16 -= (CH / 2) * TS2;
+        }
+        __syncwarp();
+
+        // ---- store: two slices per instruction, 16 pairs of consecutive codes each --------------------
+        const int j = j0 + 2 * c;
+        if (j < ncodes) {
+            const bool two = j + 1 < ncodes;
+            const uint32_t loc0 = S.map[mc][j >> I];
+            const uint32_t loc1 = two ? S.map[mc][(j + 1) >> I] : loc0;
+            const int mb0 = loc0 >> 26, off0 = loc0 & 0x3ffffffu;
+            const int mb1 = loc1 >> 26, off1 = loc1 & 0x3ffffffu;
+            int16_t *d0 = o16, *d1 = INTERLEAVED ? o16b : o16;
+            const uint32_t *tb = reinterpret_cast<const uint32_t *>(&W.tile[c * kLaneTS + h]);
+            const bool wide = !INTERLEAVED && two && mb0 == mb1 && mb0 != 0 && off1 == off0 + 1 && !(off0 & 1) &&
+                              S.even16[mc][mb0];
+            if (wide) {
+                char *p = reinterpret_cast<char *>(d0 + off0);
+                const int32_t *bb = &W.base[h * kLaneBaseStride + mb0];
+                if (act_mask == 0xffffffffu) {
+#pragma unroll
+                    for (int k = 0; k < 16; k++)
+                        *reinterpret_cast<uint32_t *>(p + 2ull * (uint32_t)bb[2 * k * kLaneBaseStride]) = tb[2 * k];
+                } else {
+#pragma unroll 4
+                    for (int k = 0; k < 16; k++)
+                        if ((act_mask >> (2 * k + h)) & 1)
+                            *reinterpret_cast<uint32_t *>(p + 2ull * (uint32_t)bb[2 * k * kLaneBaseStride]) = tb[2 * k];
+                }
+            } else {
+#pragma unroll 2
+                for (int k = 0; k < 16; k++) {
+                    const int s = 2 * k + h;
+                    if (!((act_mask >> s) & 1)) continue;
+                    const uint32_t word = tb[2 * k];
+                    if (mb0 != 0) d0[W.base[s * kLaneBaseStride + mb0] + off0] = (int16_t)(word & 0xffffu);
+                    if (two && mb1 != 0) d1[W.base[s * kLaneBaseStride + mb1] + off1] = (int16_t)(word >> 16);
+                }
+            }
+        }
+        __syncwarp();
+    }
+    VC2B_LANE_CLOSE_BAND()
+#undef VC2B_LANE_STEP16
+#undef VC2B_LANE_PAIR16
+#undef VC2B_LANE_NEXT_BAND
+#undef VC2B_LANE_SETTLE
+#undef VC2B_LANE_CLOSE_BAND
+    if ((hiacc >> 1) != 0 || (bad & 3u) != 0) ovf = true;
+    if (bad & 4u) ovf16 = true;
 }
 
 __device__ __forceinline__ void build_lane_block(const DevParams &P, LaneBlock &S, int tid, int nthreads)
@@ -614,6 +841,7 @@ __device__ __forceinline__ void build_lane_block(const DevParams &P, LaneBlock &
         S.ref_w[mc][b] = rw;
         S.ref_h[mc][b] = rh;
         S.ref_cnt[mc][b] = rw * rh;
+        S.even16[mc][b] = (b < P.nb && !(P.band[mc][b].off & 1) && !(P.band[mc][b].w & 1) && !(rw & 1)) ? 1 : 0;
         S.even_x[mc][b] = ex;
         S.even_y[mc][b] = ey;
     }
@@ -644,11 +872,11 @@ __device__ __forceinline__ void build_lane_block(const DevParams &P, LaneBlock &
 }
 
 // One LANE per slice; a warp task is 32 consecutive slices of one picture.
-template <bool LD>
+template <bool LD, bool C16>
 __global__ void __launch_bounds__(kLaneWarps * 32, 2)
 unpack_lanes_kernel(DevParams P, const uint8_t *__restrict__ data, const int64_t *__restrict__ pic_offset,
                     int npictures, const uint32_t *__restrict__ slice_offset, int32_t *__restrict__ coeffs,
-                    int32_t *__restrict__ qindex_out, int32_t *__restrict__ status)
+                    int16_t *__restrict__ coeffs16, int32_t *__restrict__ qindex_out, int32_t *__restrict__ status)
 {
     extern __shared__ __align__(16) uint8_t lane_smem[];
     LaneBlock &S = *reinterpret_cast<LaneBlock *>(lane_smem);
@@ -670,8 +898,9 @@ unpack_lanes_kernel(DevParams P, const uint8_t *__restrict__ data, const int64_t
         const long long gw = (long long)pic * nslices + n;
         const uint8_t *base = data + pic_offset[pic];
         int32_t *pc = coeffs + (size_t)pic * P.pic_coeffs;
+        int16_t *pc16 = C16 ? coeffs16 + (size_t)pic * P.pic_coeffs : nullptr;
         uint32_t maxabs = 0;
-        bool ovf = false;
+        bool ovf = false, ovf16 = false;
 
         if (!LD) {
             // hq_slice (decoder/transform_data_syntax.py:212)
@@ -685,8 +914,13 @@ unpack_lanes_kernel(DevParams P, const uint8_t *__restrict__ data, const int64_t
             for (int c = 0; c < 3; c++) {
                 const long long length = active ? (long long)P.slice_size_scaler * __ldg(base + pos) : 0;
                 pos += 1;
-                lanes_block<false>(P, c, W, S, active, sx, sy, qindex, base + pos, 0, 8 * length, pc + P.comp_off[c],
-                                   nullptr, lane, maxabs, ovf);
+                if constexpr (C16)
+                    lanes_block16<false>(P, c, W, S, active, sx, sy, qindex, base + pos, 0, 8 * length,
+                                         pc + P.comp_off[c], nullptr, pc16 + P.comp_off[c], nullptr, lane, maxabs, ovf,
+                                         ovf16);
+                else
+                    lanes_block<false>(P, c, W, S, active, sx, sy, qindex, base + pos, 0, 8 * length,
+                                       pc + P.comp_off[c], nullptr, lane, maxabs, ovf);
                 pos += length;
             }
         } else {
@@ -718,13 +952,27 @@ unpack_lanes_kernel(DevParams P, const uint8_t *__restrict__ data, const int64_t
                 }
             }
             const long long ybit = s0 * 8 + 7 + length_bits;
-            lanes_block<false>(P, 0, W, S, active, sx, sy, qindex, base + (ybit >> 3), (int)(ybit & 7), slice_y_length,
-                               pc + P.comp_off[0], nullptr, lane, maxabs, ovf);
+            if constexpr (C16)
+                lanes_block16<false>(P, 0, W, S, active, sx, sy, qindex, base + (ybit >> 3), (int)(ybit & 7),
+                                     slice_y_length, pc + P.comp_off[0], nullptr, pc16 + P.comp_off[0], nullptr, lane,
+                                     maxabs, ovf, ovf16);
+            else
+                lanes_block<false>(P, 0, W, S, active, sx, sy, qindex, base + (ybit >> 3), (int)(ybit & 7),
+                                   slice_y_length, pc + P.comp_off[0], nullptr, lane, maxabs, ovf);
             const long long cbit = ybit + slice_y_length;
-            lanes_block<true>(P, 1, W, S, active, sx, sy, qindex, base + (cbit >> 3), (int)(cbit & 7),
-                              bits_left - slice_y_length, pc + P.comp_off[1], pc + P.comp_off[2], lane, maxabs, ovf);
+            if constexpr (C16)
+                lanes_block16<true>(P, 1, W, S, active, sx, sy, qindex, base + (cbit >> 3), (int)(cbit & 7),
+                                    bits_left - slice_y_length, pc + P.comp_off[1], pc + P.comp_off[2],
+                                    pc16 + P.comp_off[1], pc16 + P.comp_off[2], lane, maxabs, ovf, ovf16);
+            else
+                lanes_block<true>(P, 1, W, S, active, sx, sy, qindex, base + (cbit >> 3), (int)(cbit & 7),
+                                  bits_left - slice_y_length, pc + P.comp_off[1], pc + P.comp_off[2], lane, maxabs,
+                                  ovf);
         }
         ovf = __any_sync(0xffffffffu, ovf);
+        if (C16) {  // status word 1 is free until finalize_status_kernel: high-pass value outside int16
+            if (__any_sync(0xffffffffu, ovf16) && lane == 0) atomicOr(&status[4 * pic + 1], 1);
+        }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) maxabs = max(maxabs, __shfl_xor_sync(0xffffffffu, maxabs, d));
         if (lane == 0 && (maxabs || ovf))
@@ -748,6 +996,20 @@ static bool lanes_eligible(const DevParams &P)
             tot += cw * ch;
             if (tot > kLaneMaxCoef) return false;
         }
+    }
+    return true;
+}
+
+// vc2b_unpack16 additionally needs every band to divide evenly between the slices
+// (slices_have_same_dimensions, pseudocode/slice_sizes.py:131) and even component offsets.
+static bool lanes16_eligible(const DevParams &P)
+{
+    if (!lanes_eligible(P)) return false;
+    if (P.pic_coeffs & 1) return false;
+    for (int c = 0; c < 3; c++) {
+        if (P.comp_off[c] & 1) return false;
+        for (int b = 0; b < P.nb; b++)
+            if (P.band[c][b].w % P.slices_x || P.band[c][b].h % P.slices_y) return false;
     }
     return true;
 }

@@ -12,7 +12,13 @@ import numpy as np
 from . import capi
 from .params import Geometry
 
-PAD = 64  # readable slack after the stream bytes (the kernels fetch aligned words)
+PAD = 64  # readable slack after the stream bytes (the kernels fetch aligned 16-byte pieces)
+
+# Default for BatchCodec(coeff16=None): whether decoders stage the high-pass coefficients as int16 between the
+# unpack and the IDWT where the library supports it (vc2b_coeff16_supported).  Results are identical: a picture
+# whose coefficients do not fit is decoded again through the int32 plane.  The compat layer (pseudocode.py)
+# hands coefficients to the reference as int32 and always uses the int32 plane.
+DEFAULT_COEFF16 = False
 
 
 class StreamError(Exception):
@@ -27,6 +33,7 @@ class StreamError(Exception):
             capi.ST_UNEXPECTED_END_OF_STREAM: "UnexpectedEndOfStream",
             capi.ST_INVALID_SLICE_Y_LENGTH: "InvalidSliceYLength",
             capi.ST_INT32_ENVELOPE: "value outside the int32 envelope",
+            capi.ST_COEFF16_RANGE: "coefficient outside the int16 plane (decode again with coeff16=False)",
         }
         Exception.__init__(
             self, "picture %d, slice %d: %s" % (picture, bad_slice, names.get(status, status))
@@ -63,7 +70,7 @@ class BatchCodec(object):
     """Buffers and launch sequence for batches of up to ``max_pictures`` pictures that share one
     parameter set.  All device work is enqueued on ``stream`` (default: torch's current)."""
 
-    def __init__(self, params, max_pictures, max_stream_bytes=None, device="cuda:0", group=128):
+    def __init__(self, params, max_pictures, max_stream_bytes=None, device="cuda:0", group=128, coeff16=None):
         torch = _torch()
         self.torch = torch
         self.lib = capi.lib()
@@ -73,8 +80,14 @@ class BatchCodec(object):
         self.max_pictures = int(max_pictures)
         g = self.g
         dev = self.device
+        if coeff16 is None:
+            coeff16 = DEFAULT_COEFF16
+        self.coeff16 = bool(coeff16) and bool(self.lib.vc2b_coeff16_supported(C.byref(params)))
+        self._plane32 = set()  # pictures of the last decode whose coefficients are all in the int32 plane
         with torch.cuda.device(dev):
             self.coeffs = torch.empty(self.max_pictures * g.picture_coeffs, dtype=torch.int32, device=dev)
+            self.coeffs16 = (torch.empty(self.max_pictures * g.picture_coeffs, dtype=torch.int16, device=dev)
+                             if self.coeff16 else None)
             self.pictures = torch.empty(self.max_pictures * g.picture_samples, dtype=torch.uint16, device=dev)
             self.group = max(1, min(int(group), self.max_pictures))
             self.scratch = torch.empty(max(g.scratch_bytes * self.group, 16), dtype=torch.uint8, device=dev)
@@ -143,10 +156,13 @@ class BatchCodec(object):
 
     def decode_streams(self, streams, stream=None, check=True):
         """End-to-end decode of host streams: H2D, slice index, unpack+dequant, IDWT+clip+offset.
-        Returns the device picture tensor view [n, picture_samples] (uint16)."""
+        Returns the device picture tensor view [n, picture_samples] (uint16).  With the int16 coefficient
+        plane, pictures that do not fit it are decoded again through the int32 plane before returning."""
         n = len(streams)
         host, offs = self.pack_host_streams(streams)
         self.decode_host(host, offs, n, stream)
+        if self.coeff16:
+            self.redo_coeff16(self.status_host(n, stream), stream=stream)
         if check:
             self.check_status(n, stream)
         return self.pictures[: n * self.g.picture_samples].view(n, self.g.picture_samples)
@@ -159,9 +175,13 @@ class BatchCodec(object):
         self.upload_streams(host, offs, n, stream)
         self.unpack_device(self.data, self.pic_offset, n, stream)
 
-    def unpack_device(self, d_data, d_pic_offset, n, stream=None, first=0):
-        """Slice index + unpack of ``n`` pictures whose transform data is resident in HBM."""
+    def unpack_device(self, d_data, d_pic_offset, n, stream=None, first=0, coeff16=None):
+        """Slice index + unpack of ``n`` pictures whose transform data is resident in HBM (``d_pic_offset``:
+        the offsets of those pictures; results go to picture slots ``first``..)."""
         L, p, g = self.lib, self.p, self.g
+        c16 = self.coeff16 if coeff16 is None else (coeff16 and self.coeff16)
+        for i in range(first, first + n):  # which plane holds picture i's high-pass coefficients
+            self._plane32.discard(i) if c16 else self._plane32.add(i)
         coeffs = self.coeffs[first * g.picture_coeffs:]
         status = self.status[first * 4:]
         qindex = self.qindex[first * g.num_slices:]
@@ -172,23 +192,53 @@ class BatchCodec(object):
                 capi.check("vc2b_hq_slice_offsets",
                            L.vc2b_hq_slice_offsets(C.byref(p), _ptr(d_data), _ptr(d_pic_offset), n, _ptr(so),
                                                    _ptr(status), sp))
-            capi.check("vc2b_unpack",
-                       L.vc2b_unpack(C.byref(p), _ptr(d_data), _ptr(d_pic_offset), n, _ptr(so), _ptr(coeffs),
-                                     _ptr(qindex), _ptr(status), sp))
+            if c16:
+                capi.check("vc2b_unpack16",
+                           L.vc2b_unpack16(C.byref(p), _ptr(d_data), _ptr(d_pic_offset), n, _ptr(so), _ptr(coeffs),
+                                           _ptr(self.coeffs16[first * g.picture_coeffs:]), _ptr(qindex),
+                                           _ptr(status), sp))
+            else:
+                capi.check("vc2b_unpack",
+                           L.vc2b_unpack(C.byref(p), _ptr(d_data), _ptr(d_pic_offset), n, _ptr(so), _ptr(coeffs),
+                                         _ptr(qindex), _ptr(status), sp))
 
-    def decode_device(self, d_data, d_pic_offset, n, stream=None, first=0):
-        """Decode ``n`` pictures whose transform data is already resident in HBM."""
-        self.unpack_device(d_data, d_pic_offset, n, stream, first)
-        self.idwt_device(n, stream, first)
+    def decode_device(self, d_data, d_pic_offset, n, stream=None, first=0, coeff16=None):
+        """Decode ``n`` pictures whose transform data is already resident in HBM.  With the int16 plane a
+        picture may come back with status ST_COEFF16_RANGE: ``redo_coeff16`` decodes those again."""
+        self.unpack_device(d_data, d_pic_offset, n, stream, first, coeff16)
+        self.idwt_device(n, stream, first, coeff16)
 
-    def idwt_device(self, n, stream=None, first=0):
+    def idwt_device(self, n, stream=None, first=0, coeff16=None):
         L, p, g = self.lib, self.p, self.g
+        c16 = self.coeff16 if coeff16 is None else (coeff16 and self.coeff16)
         coeffs = self.coeffs[first * g.picture_coeffs:]
         pics = self.pictures[first * g.picture_samples:]
         with self._on(stream):
-            capi.check("vc2b_idwt",
-                       L.vc2b_idwt(C.byref(p), _ptr(coeffs), n, _ptr(pics), _ptr(self.scratch),
-                                   self.scratch.numel(), self._stream_ptr(stream)))
+            if c16:
+                capi.check("vc2b_idwt16",
+                           L.vc2b_idwt16(C.byref(p), _ptr(coeffs), _ptr(self.coeffs16[first * g.picture_coeffs:]), n,
+                                         _ptr(pics), _ptr(self.scratch), self.scratch.numel(),
+                                         self._stream_ptr(stream)))
+            else:
+                capi.check("vc2b_idwt",
+                           L.vc2b_idwt(C.byref(p), _ptr(coeffs), n, _ptr(pics), _ptr(self.scratch),
+                                       self.scratch.numel(), self._stream_ptr(stream)))
+
+    def redo_coeff16(self, st, d_data=None, d_pic_offset=None, stream=None):
+        """Pictures whose status (host array [n, 4] from ``status_host``) is ST_COEFF16_RANGE are decoded
+        again through the int32 plane, in place; ``st`` is updated.  Returns the pictures redone."""
+        redone = [i for i in range(st.shape[0]) if st[i, 0] == capi.ST_COEFF16_RANGE]
+        if not redone:
+            return redone
+        d_data = self.data if d_data is None else d_data
+        d_pic_offset = self.pic_offset if d_pic_offset is None else d_pic_offset
+        for i in redone:
+            self.decode_device(d_data, d_pic_offset[i:], 1, stream, first=i, coeff16=False)
+        with self._on(stream):
+            fresh = self.status[: 4 * st.shape[0]].cpu().numpy().reshape(-1, 4)
+        for i in redone:
+            st[i] = fresh[i]
+        return redone
 
     def check_status(self, n, stream=None):
         st = self.status_host(n, stream)
@@ -344,10 +394,20 @@ class BatchCodec(object):
         return [flat[g.plane_off[c]: g.plane_off[c] + g.dims[c][0] * g.dims[c][1]].reshape(g.dims[c][1], g.dims[c][0])
                 for c in range(3)]
 
-    def coeff_components(self, i):
+    def coeff_components(self, i, coeff16=None):
+        """Host copies of picture i's coefficients as [Y, C1, C2] int32 arrays (with the int16 plane: the
+        level-0 band from the int32 buffer, everything else widened from the int16 buffer)."""
         g = self.g
+        c16 = (self.coeff16 and i not in self._plane32) if coeff16 is None else (coeff16 and self.coeff16)
         with self._on(None):
             flat = self.coeffs[i * g.picture_coeffs:(i + 1) * g.picture_coeffs].cpu().numpy()
+            if c16:
+                wide = self.coeffs16[i * g.picture_coeffs:(i + 1) * g.picture_coeffs].cpu().numpy().astype(np.int32)
+                for c in range(3):
+                    b0 = g.bands[c][0]
+                    lo, cnt = g.comp_off[c] + b0["off"], b0["w"] * b0["h"]
+                    wide[lo:lo + cnt] = flat[lo:lo + cnt]
+                flat = wide
         return [flat[g.comp_off[c]: g.comp_off[c] + g.comp_coeffs[c]] for c in range(3)]
 
 
@@ -384,7 +444,7 @@ class SequenceDecoder(object):
     This is the throughput form of the per-picture entry points the reference calls in
     decoder/stream.py:128-133 (picture_parse's transform_data, then picture_decode)."""
 
-    def __init__(self, params, chunk=8, nstreams=3, max_chunk_bytes=1 << 20, device="cuda:0"):
+    def __init__(self, params, chunk=8, nstreams=3, max_chunk_bytes=1 << 20, device="cuda:0", coeff16=True):
         torch = _torch()
         self.torch = torch
         self.p = params
@@ -392,9 +452,10 @@ class SequenceDecoder(object):
         self.device = torch.device(device)
         with torch.cuda.device(self.device):
             self.streams = [torch.cuda.Stream(device=self.device) for _ in range(nstreams)]
-            self.codecs = [BatchCodec(params, self.chunk, max_chunk_bytes, device, group=self.chunk)
+            self.codecs = [BatchCodec(params, self.chunk, max_chunk_bytes, device, group=self.chunk, coeff16=coeff16)
                            for _ in range(nstreams)]
         self.g = self.codecs[0].g
+        self.status_host = None  # pinned [pictures, 4] int32: every picture's status words (decode)
 
     @property
     def launches(self):
@@ -423,12 +484,39 @@ class SequenceDecoder(object):
         torch = self.torch
         S = self.g.picture_samples
         ns = len(self.streams)
+        total = sum(c[1] for c in chunks)
+        if self.status_host is None or self.status_host.shape[0] < total:
+            self.status_host = torch.zeros((total, 4), dtype=torch.int32).pin_memory()
         for k, (i0, n, hbytes, rel) in enumerate(chunks):
             s = self.streams[k % ns]
             codec = self.codecs[k % ns]
             codec.decode_host(hbytes, rel, n, s)
             with torch.cuda.stream(s):
                 out_host[i0:i0 + n].copy_(codec.pictures[: n * S].view(n, S), non_blocking=True)
+                self.status_host[i0:i0 + n].copy_(codec.status[: 4 * n].view(n, 4), non_blocking=True)
+
+    def finish(self, chunks, out_host):
+        """After ``synchronize()``: pictures that did not fit the int16 coefficient plane are decoded again
+        through the int32 plane (synchronously) and written to ``out_host``.  Returns the host status array
+        [pictures, 4] of the sequence."""
+        torch = self.torch
+        S = self.g.picture_samples
+        total = sum(c[1] for c in chunks)
+        st = self.status_host[:total].numpy()
+        for k, (i0, n, hbytes, rel) in enumerate(chunks):
+            bad = [i for i in range(n) if st[i0 + i, 0] == capi.ST_COEFF16_RANGE]
+            if not bad:
+                continue
+            codec = self.codecs[0]
+            s = self.streams[0]
+            codec.upload_streams(hbytes, rel, n, s)
+            for i in bad:
+                codec.decode_device(codec.data, codec.pic_offset[i:], 1, s, first=i, coeff16=False)
+                with torch.cuda.stream(s):
+                    out_host[i0 + i].copy_(codec.pictures[i * S:(i + 1) * S], non_blocking=True)
+                    self.status_host[i0 + i].copy_(codec.status[4 * i:4 * i + 4], non_blocking=True)
+            s.synchronize()
+        return st
 
     def fork_from(self, stream):
         """Make every worker stream wait for ``stream`` (start of a timed region)."""
