@@ -35,7 +35,7 @@ constexpr int kLaneTS = 34;              // tile row stride: conflict-free for b
 struct __align__(16) LaneWarp {          // per-warp shared memory
     int32_t tile[kLaneChunk * kLaneTS];  // [code of the chunk][slice]
     int32_t base[32 * kLaneBaseStride];  // [slice][band]: offset of the rectangle in the component
-    uint4 stage[2][32];                  // [slot][lane]: the lane's bitstream, 16 bytes per slot (lane_fetch)
+    uint4 stage[32][2];                  // [lane][slot]: the lane's bitstream, 16 bytes per slot (lane_fetch)
 };
 
 struct __align__(16) LaneBlock {                       // per-CTA shared memory
@@ -140,16 +140,14 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
 // cp.async, one piece ahead of the one being read.  (Per-lane 4-byte global loads were the largest stall of
 // this kernel -- every load touches 32 different L1 lines and its scoreboard had to be waited for at the
 // top of every group of codes; a cp.async group is waited for four refills after it was issued.)
-constexpr int kLaneSlotStride = 32 * 16;  // bytes between the two slots of a lane
-
 struct LaneReader {
     const uint4 *cp;      // next 16-byte piece of the stream to stage
     uint64_t buf;         // bit buffer, next bit at the top; bits below `avail` are zero
     uint32_t ahead;       // the word after the buffer (raw), read from the slots one refill early
-    uint32_t slot;        // shared-memory address of the lane's first slot
-    uint32_t wi;          // next word to read from the slots (bit 2: slot, bits 0-1: word)
+    uint32_t slot;        // shared-memory address of the lane's two slots (32 consecutive bytes)
+    uint32_t wo;          // byte offset (0, 4, .. 28) of the next word to read from the slots
     int avail;            // valid bits in buf
-    int remaining;        // bits of the bounded block at and after word wi (<= 0: past its end)
+    int remaining;        // bits of the bounded block at and after the next word to read (<= 0: past its end)
 };
 
 __device__ __forceinline__ void lane_stage(uint32_t dst, const uint4 *src)
@@ -157,35 +155,33 @@ __device__ __forceinline__ void lane_stage(uint32_t dst, const uint4 *src)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 
-__device__ __forceinline__ uint32_t lane_word_addr(const LaneReader &R, uint32_t i)
+// Every fourth word: the slot just read to its end is free -- stage the piece after the other slot's into it.
+// The group is committed even when it is empty (the block ends before that piece), so that "all groups but
+// the newest" always covers the slot about to be read.
+__device__ __forceinline__ void lane_next_piece(LaneReader &R)
 {
-    return R.slot + ((i & 4u) << 7) + ((i & 3u) << 2);
+    if (R.remaining > 128) lane_stage(R.slot + (R.wo ^ 16u), R.cp);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    R.cp++;
 }
 
-// Takes the next word of the block into `ahead` (nothing is read past its end) and, when that was the
-// last word of a slot, stages the piece after the other slot's into it.
+// Takes the next word of the block into `ahead`.  Past the end of the block the word is stale shared memory:
+// lane_ahead_bits turns it into ones.
 __device__ __forceinline__ void lane_fetch(LaneReader &R)
 {
-    // every group but the newest is complete: the newest fills the slot that is not being read
-    asm volatile("cp.async.wait_group 1;" ::: "memory");
-    if (R.remaining > 0) R.ahead = lds_u32(lane_word_addr(R, R.wi));
-    R.wi++;
+    R.ahead = lds_u32(R.slot + R.wo);
+    R.wo = (R.wo + 4u) & 31u;
     R.remaining -= 32;
-    if ((R.wi & 3u) == 0) {
-        if (R.remaining > 128) {
-            lane_stage(R.slot + (((R.wi & 4u) ^ 4u) << 7), R.cp);
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        }
-        R.cp++;
-    }
+    if ((R.wo & 15u) == 0) lane_next_piece(R);
 }
 
 // The word fetched last as 32 bits of the bounded block: ones past its end (decoder/io.py:246-252).
 __device__ __forceinline__ uint32_t lane_ahead_bits(const LaneReader &R)
 {
-    const int rem = R.remaining + 32;   // bits of the block at and after the fetched word
     uint32_t w = __byte_perm(R.ahead, 0, 0x0123);
-    if (rem < 32) w |= 0xffffffffu >> max(rem, 0);
+    if (__builtin_expect(R.remaining < 0, 0))   // fewer than 32 bits of the block in the fetched word
+        w |= 0xffffffffu >> max(R.remaining + 32, 0);
     return w;
 }
 
@@ -206,34 +202,30 @@ __device__ __forceinline__ void lane_reader_init(LaneReader &R, uint32_t slot, c
     const uintptr_t addr = reinterpret_cast<uintptr_t>(blk);
     R.cp = reinterpret_cast<const uint4 *>(addr & ~(uintptr_t)15);
     R.slot = slot;
-    const uint32_t w0 = (uint32_t)(addr & 15) >> 2;
-    const int skip = (int)(addr & 3) * 8 + bit_off;   // <= 31
+    const uint32_t w0 = (uint32_t)(addr & 15);       // byte offset of the first word within its piece
+    const int skip = (int)(addr & 3) * 8 + bit_off;  // <= 31
     long long rem = nbits + skip;
-    if (rem > (1LL << 30)) rem = 1LL << 30;           // a slice of this kernel never reads that far
+    if (rem > (1LL << 30)) rem = 1LL << 30;          // a slice of this kernel never reads that far
     R.remaining = active ? (int)rem : 0;
     // the first two pieces are staged together (one load latency); they hold the first three words
     if (R.remaining > 0) {
         lane_stage(slot, R.cp);
-        lane_stage(slot + kLaneSlotStride, R.cp + 1);
+        lane_stage(slot + 16, R.cp + 1);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     R.cp += 2;
-    uint32_t raw0 = 0, raw1 = 0;
-    R.ahead = 0;
-    if (R.remaining > 0) raw0 = lds_u32(lane_word_addr(R, w0));
-    if (R.remaining > 32) raw1 = lds_u32(lane_word_addr(R, w0 + 1));
-    if (R.remaining > 64) R.ahead = lds_u32(lane_word_addr(R, w0 + 2));
-    uint32_t wd0 = __byte_perm(raw0, 0, 0x0123), wd1 = __byte_perm(raw1, 0, 0x0123);
+    const uint32_t wa = w0 & 12u;
+    uint32_t wd0 = __byte_perm(lds_u32(slot + wa), 0, 0x0123);
+    uint32_t wd1 = __byte_perm(lds_u32(slot + wa + 4), 0, 0x0123);
+    R.ahead = lds_u32(slot + wa + 8);
     if (R.remaining < 32) wd0 |= 0xffffffffu >> max(R.remaining, 0);
     if (R.remaining < 64) wd1 |= 0xffffffffu >> max(R.remaining - 32, 0);
-    R.wi = w0 + 3;
+    R.wo = wa + 12;          // <= 24: still inside the two slots
     R.remaining -= 96;
-    if (R.wi >= 4) {  // the first slot is used up already: stage the third piece into it
-        if (R.remaining > 32 * (int)(8 - R.wi)) {
-            lane_stage(slot, R.cp);
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        }
+    if (R.wo >= 16) {        // the first slot is used up already: stage the third piece into it
+        if (R.remaining > 4 * (int)(64 - 2 * R.wo)) lane_stage(slot, R.cp);   // bits at and after word 8
+        asm volatile("cp.async.commit_group;" ::: "memory");
         R.cp++;
     }
     R.buf = (((uint64_t)wd0 << 32) | wd1) << skip;
@@ -393,7 +385,7 @@ __device__ __forceinline__ void lanes_block(const DevParams &P, const int comp, 
     const bool my_match = match || !active;
 
     LaneReader R;
-    lane_reader_init(R, (uint32_t)__cvta_generic_to_shared(&W.stage[0][lane]), blk, bit_off, nbits, active);
+    lane_reader_init(R, (uint32_t)__cvta_generic_to_shared(&W.stage[lane][0]), blk, bit_off, nbits, active);
 
     int b = -1, next = 0;
     uint32_t qf = 0, qo = 0, maxmag = 0;
@@ -513,14 +505,15 @@ __device__ __forceinline__ void lanes_block(const DevParams &P, const int comp, 
                         VC2B_LANE_STEP(1, false)
                         VC2B_LANE_STEP(2, false)
                         VC2B_LANE_STEP(3, false)
+                        VC2B_LANE_SETTLE()
                     }
                 } else {
                     VC2B_LANE_STEP(0, false)
                     VC2B_LANE_STEP(1, true)
                     VC2B_LANE_STEP(2, true)
                     VC2B_LANE_STEP(3, true)
+                    VC2B_LANE_SETTLE()
                 }
-                VC2B_LANE_SETTLE()
                 lane_refill(R);
                 j0 += 4;
                 tile += 4 * kLaneTS;
@@ -633,7 +626,7 @@ __device__ __forceinline__ void lanes_block16(const DevParams &P, const int comp
     if (act_mask == 0) return;
 
     LaneReader R;
-    lane_reader_init(R, (uint32_t)__cvta_generic_to_shared(&W.stage[0][lane]), blk, bit_off, nbits, active);
+    lane_reader_init(R, (uint32_t)__cvta_generic_to_shared(&W.stage[lane][0]), blk, bit_off, nbits, active);
 
     int b = -1, next = 0;
     uint32_t qf = 0, qo = 0, maxmag = 0;
@@ -747,14 +740,15 @@ __device__ __forceinline__ void lanes_block16(const DevParams &P, const int comp
                         VC2B_LANE_STEP16(1, false)
                         VC2B_LANE_STEP16(2, false)
                         VC2B_LANE_STEP16(3, false)
+                        VC2B_LANE_SETTLE()
                     }
                 } else {
                     VC2B_LANE_STEP16(0, false)
                     VC2B_LANE_STEP16(1, true)
                     VC2B_LANE_STEP16(2, true)
                     VC2B_LANE_STEP16(3, true)
+                    VC2B_LANE_SETTLE()
                 }
-                VC2B_LANE_SETTLE()
                 lane_refill(R);
                 j0 += 4;
                 t16 += 2 * TS2;
