@@ -100,6 +100,8 @@ def parse_args():
     ap.add_argument("--pictures", type=int, default=0, help="override pictures per sequence")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-config-sweep", action="store_true",
+                    help="skip the stage timings of the other BASELINE configurations (stages_by_config)")
     ap.add_argument("--int32-plane", action="store_true",
                     help="stage coefficients as int32 between unpack and IDWT (default: int16 high-pass bands)")
     ap.add_argument("--chunk", type=int, default=8)
@@ -508,6 +510,59 @@ def timed(rig, steps, warmup, step_fn, nmarks):
     return e0.elapsed_time(e1), stage_ms
 
 
+def decode_stages_of(rig, name, npictures, steps=4, warmup=2, coeff16=True):
+    """Device-timed unpack / IDWT stages of another BASELINE configuration (one resident batch), so that
+    every configuration has a driver-run figure; the pictures of the first two (noise, ramp) are checked
+    against the C oracle's decode when ``check`` streams are returned."""
+    from vc2_conformance_b200.device import BatchCodec
+
+    torch = rig.torch
+    w = make_workload(name, npictures)
+    p, NP, S = w["p"], w["pictures"], w["samples"]
+    codec = BatchCodec(p, NP, max_stream_bytes=NP * (w["picture_bytes"] + 64), device=rig.dev, group=128,
+                       coeff16=coeff16)
+    distinct = min(NP, 4)
+    pics = np.stack([__import__("synth").flat_picture(synth_picture(dict(w, pictures=distinct), rig.rank, i))
+                     for i in range(distinct)])
+    streams = codec.encode_pictures(pics, w["picture_bytes"])
+    streams = [streams[i % distinct] for i in range(NP)]
+    host, offs = codec.pack_host_streams(streams)
+    codec._reserve_data(host.numel())
+    codec.data[: host.numel()].copy_(host)
+    codec.pic_offset[: NP + 1].copy_(offs)
+    torch.cuda.synchronize()
+    codec.decode_device(codec.data, codec.pic_offset, NP)
+    assert (codec.status_host(NP)[:, 0] == 0).all(), "decode status not OK (%s)" % name
+
+    def step(mark):
+        codec.unpack_device(codec.data, codec.pic_offset, NP)
+        mark()
+        codec.idwt_device(NP)
+        mark()
+
+    _ms, (ms_u, ms_i) = timed(rig, steps, warmup, step, 2)
+    peak, _src = measured_peak()
+    padded = sum(codec.g.comp_coeffs)
+    ub = (int(offs[NP]) + 4 * padded * NP) / (ms_u / 1000.0) / 1e9
+    ib = ((4 * padded + 2 * S) * NP) / (ms_i / 1000.0) / 1e9
+    out = {"workload": w["name"], "pictures": NP, "coefficient_plane": "int16" if codec.coeff16 else "int32",
+           "unpack_us_per_picture": 1000.0 * ms_u / NP, "unpack_frac": ub / peak,
+           "idwt_us_per_picture": 1000.0 * ms_i / NP, "idwt_frac": ib / peak,
+           "pictures_per_s": NP / ((ms_u + ms_i) / 1000.0)}
+    # parity of what was just timed: the first picture of each kind against the oracle
+    O = _oracle()
+    import synth
+    po = synth.oracle_params(p)
+    for i in range(min(2, distinct)):
+        st, dec, _consumed = O.decode_picture(po, streams[i])
+        got = codec.picture_planes(i)
+        assert st == 0 and all((got[c] == dec[c]).all() for c in range(3)), "GPU picture differs from the oracle (%s)" % name
+    out["checked"] = "pictures 0..%d bit-exact against the oracle" % (min(2, distinct) - 1)
+    del codec
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_decode(args):
     import ctypes as C
 
@@ -615,6 +670,12 @@ def run_decode(args):
             "numa_bound_cpus": rig.numa_cpus,
             "checked": "all %d pictures equal to the resident path" % NP,
         }
+    # ---- the other decoder configurations of BASELINE.json (device-timed stages, one resident batch each) ----
+    by_config = None
+    if rank == 0 and world == 1 and not args.no_config_sweep and args.workload == "cfg2":
+        by_config = {}
+        for name, npic in (("cfg1", 192), ("cfg3", 256), ("cfg4", 128)):
+            by_config[name] = decode_stages_of(rig, name, npic, coeff16=not args.int32_plane)
     rig.sampler.stop()
     clocks = rig.sampler.summary(rig.windows)
 
@@ -689,6 +750,7 @@ def run_decode(args):
             "roofline": roofline,
             "stages": stages,
             "stages_by_content": by_content,
+            "stages_by_config": by_config,
             "cpu_baseline": cpu,
             "cpu_baseline_reference": cpu_ref,
             "gpu_launches": launches,

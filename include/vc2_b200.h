@@ -150,9 +150,12 @@ int vc2b_dc_prediction(const vc2b_params *p, int32_t *d_coeffs, int npictures, i
  *               in flight per launch */
 int vc2b_idwt(const vc2b_params *p, const int32_t *d_coeffs, int npictures, uint16_t *d_pictures,
               void *d_scratch, int64_t scratch_bytes, void *stream);
-/* picture_decode from the int16 coefficient plane of vc2b_unpack16 (d_coeffs supplies the level-0 bands). */
+/* picture_decode from the int16 coefficient plane of vc2b_unpack16 (d_coeffs supplies the level-0 bands).
+ * The intermediate bands between the levels are int16 as well (half the scratch bytes of vc2b_idwt suffice);
+ * a picture with an intermediate value outside int16 gets d_status[4*i] = VC2B_ST_COEFF16_RANGE (only over
+ * VC2B_ST_OK) and must be decoded again with vc2b_unpack + vc2b_idwt.  d_status: the words vc2b_unpack16 wrote. */
 int vc2b_idwt16(const vc2b_params *p, const int32_t *d_coeffs, const int16_t *d_coeffs16, int npictures,
-                uint16_t *d_pictures, void *d_scratch, int64_t scratch_bytes, void *stream);
+                uint16_t *d_pictures, void *d_scratch, int64_t scratch_bytes, int32_t *d_status, void *stream);
 /* idwt (:88) alone for ONE component: no crop, clip or offset; int32 out, padded dimensions. */
 int vc2b_idwt_raw(const vc2b_params *p, int comp, const int32_t *d_coeffs, int32_t *d_out,
                   void *d_scratch, int64_t scratch_bytes, void *stream);

@@ -315,25 +315,27 @@ def test_coeff16_plane(case, group):
 
 
 def test_coeff16_overflow_is_redone_through_the_int32_plane():
-    """A lossless 16-bit noise picture has high-pass coefficients beyond int16: the int16 plane reports
-    VC2B_ST_COEFF16_RANGE for it, and decode_streams / SequenceDecoder.finish decode it again through the
-    int32 plane; pictures that fit (the ramp) are left alone."""
+    """A lossless 16-bit noise picture has high-pass coefficients beyond int16 (flagged by the unpack), a 16-bit
+    ramp has intermediate low-pass bands beyond int16 (flagged by the IDWT level that produces them): both come
+    back as VC2B_ST_COEFF16_RANGE and decode_streams / SequenceDecoder.finish decode them again through the
+    int32 planes; a picture that fits is left alone."""
     from vc2_conformance_b200 import capi
     from vc2_conformance_b200.device import BatchCodec, SequenceDecoder
 
     W, H = 512, 256
     p = _mk(luma_width=W, luma_height=H, color_diff_width=W // 2, color_diff_height=H, luma_depth=16,
             wavelet_index=0, dwt_depth=3, slices_x=16, slices_y=32, slice_size_scaler=8)
-    pics = [synth.noise_picture(p, 50), synth.ramp_picture(p, 51), synth.noise_picture(p, 52),
-            synth.ramp_picture(p, 53)]
+    rng = np.random.default_rng(7)
+    quiet = [(32768 + rng.integers(-400, 400, size=(H, w))).astype(np.uint16) for w in (W, W // 2, W // 2)]
+    pics = [synth.noise_picture(p, 50), synth.ramp_picture(p, 51), quiet, synth.noise_picture(p, 53)]
     streams, decoded = _oracle_streams(p, pics, [None] * len(pics))
     codec = BatchCodec(p, len(pics), coeff16=True)
     assert codec.coeff16
     host, offs = codec.pack_host_streams(streams)
     codec.decode_host(host, offs, len(pics))
     st = codec.status_host(len(pics))
-    assert list(st[:, 0]) == [capi.ST_COEFF16_RANGE, capi.ST_OK, capi.ST_COEFF16_RANGE, capi.ST_OK]
-    assert codec.redo_coeff16(st) == [0, 2]
+    assert list(st[:, 0]) == [capi.ST_COEFF16_RANGE, capi.ST_COEFF16_RANGE, capi.ST_OK, capi.ST_COEFF16_RANGE]
+    assert codec.redo_coeff16(st) == [0, 1, 3]
     assert (st[:, 0] == capi.ST_OK).all()
     for i in range(len(pics)):
         planes = codec.picture_planes(i)

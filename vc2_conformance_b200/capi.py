@@ -119,7 +119,7 @@ SIGNATURES = {
     "vc2b_set_unpack_kernel": (_i, [_i]),
     "vc2b_dc_prediction": (_i, [_PP, _vp, _i, _i, _vp]),
     "vc2b_idwt": (_i, [_PP, _vp, _i, _vp, _vp, _i64, _vp]),
-    "vc2b_idwt16": (_i, [_PP, _vp, _vp, _i, _vp, _vp, _i64, _vp]),
+    "vc2b_idwt16": (_i, [_PP, _vp, _vp, _i, _vp, _vp, _i64, _vp, _vp]),
     "vc2b_idwt_raw": (_i, [_PP, _i, _vp, _vp, _vp, _i64, _vp]),
     "vc2b_dwt": (_i, [_PP, _vp, _i, _vp, _vp, _i64, _vp]),
     "vc2b_dwt_raw": (_i, [_PP, _i, _vp, _vp, _vp, _i64, _vp]),

@@ -34,6 +34,8 @@ struct LevelArgs {
     const int32_t *hb[3][3];        // HL, LH, HH (or H in slot 0 for horizontal-only levels)
     long long hb_pic_stride;        // elements (int32, or int16 when hb16)
     int32_t hb16;                   // 1: hb[][] address int16 coefficients (vc2b_unpack16's plane; wide kernel only)
+    int32_t ll16, out16;            // 1: ll[] / out[] address int16 samples (vc2b_idwt16's intermediate bands)
+    int32_t *status;                // out16: per-picture status words (4 per picture) for VC2B_ST_COEFF16_RANGE
     int32_t w[3], h[3];             // input LL dimensions
     // output
     int32_t *out[3];                // int32 output (intermediate LL or raw final), row stride = 2w
@@ -483,8 +485,12 @@ static void plan_scratch(const DevParams &P, int c0, int c1, ScratchPlan *sp)
 // level on B200.  What does cut the DRAM traffic of this stage is the int16 coefficient plane.
 static int run_idwt(const DevParams &P, int c0, int c1, const int32_t *coeffs, const int16_t *coeffs16,
                     long long coeff_pic_stride, int npic, uint16_t *pictures, int32_t *raw_out, int32_t *scratch,
-                    const ScratchPlan &sp, cudaStream_t s)
+                    const ScratchPlan &sp, int32_t *status, cudaStream_t s)
 {
+    // with the int16 coefficient plane the intermediate bands are int16 too (same element offsets in the
+    // scratch buffer); a level that produces a value outside int16 flags the picture in `status`
+    int16_t *scratch16 = reinterpret_cast<int16_t *>(scratch);
+    const bool s16 = coeffs16 != nullptr;
     const int top = P.dwt_depth + P.dwt_depth_ho;
     const int ncomp = c1 - c0;
     const long long scratch_pic = sp.size_a + sp.size_b;
@@ -492,7 +498,8 @@ static int run_idwt(const DevParams &P, int c0, int c1, const int32_t *coeffs, c
     memset(&A, 0, sizeof(A));
     A.ncomp = ncomp;
     A.hb_pic_stride = coeff_pic_stride;
-    A.hb16 = coeffs16 ? 1 : 0;
+    A.hb16 = s16 ? 1 : 0;
+    A.status = status;
     A.pic_pic_stride = P.pic_samples;
     A.shift = get_filter(P.wavelet_index_ho).shift;
     for (int i = 0; i < ncomp; i++) {
@@ -540,17 +547,21 @@ static int run_idwt(const DevParams &P, int c0, int c1, const int32_t *coeffs, c
                 A.ll_pic_stride[i] = coeff_pic_stride;
             } else {
                 const int rsel = ((top - 1) - (n - 1)) & 1;
-                A.ll[i] = scratch + (rsel == 0 ? sp.comp_off_a[c] : sp.size_a + sp.comp_off_b[c]);
+                const long long off = rsel == 0 ? sp.comp_off_a[c] : sp.size_a + sp.comp_off_b[c];
+                A.ll[i] = s16 ? reinterpret_cast<const int32_t *>(scratch16 + off) : scratch + off;
                 A.ll_pic_stride[i] = scratch_pic;
             }
             if (!last) {
-                A.out[i] = scratch + (wsel == 0 ? sp.comp_off_a[c] : sp.size_a + sp.comp_off_b[c]);
+                const long long off = wsel == 0 ? sp.comp_off_a[c] : sp.size_a + sp.comp_off_b[c];
+                A.out[i] = s16 ? reinterpret_cast<int32_t *>(scratch16 + off) : scratch + off;
                 A.out_pic_stride[i] = scratch_pic;
             } else {
                 A.out[i] = raw_out;
                 A.out_pic_stride[i] = 0;
             }
         }
+        A.ll16 = (s16 && n > 1) ? 1 : 0;
+        A.out16 = (s16 && !last) ? 1 : 0;
         A.final_u16 = (last && pictures) ? 1 : 0;
         A.hint_loads = 0;
         A.hint_hb = A.hint_ll = kL2Normal;
@@ -625,7 +636,7 @@ int vc2b_idwt(const vc2b_params *p, const int32_t *d_coeffs, int npictures, uint
     for (int i = 0; i < npictures; i += group) {
         const int n = (npictures - i < group) ? npictures - i : group;
         st = run_idwt(P, 0, 3, d_coeffs + (long long)i * P.pic_coeffs, nullptr, P.pic_coeffs, n,
-                      d_pictures + (long long)i * P.pic_samples, nullptr, (int32_t *)d_scratch, sp,
+                      d_pictures + (long long)i * P.pic_samples, nullptr, (int32_t *)d_scratch, sp, nullptr,
                       (cudaStream_t)stream);
         if (st) return st;
     }
@@ -640,19 +651,20 @@ int vc2b_coeff16_supported(const vc2b_params *p)
 }
 
 int vc2b_idwt16(const vc2b_params *p, const int32_t *d_coeffs, const int16_t *d_coeffs16, int npictures,
-                uint16_t *d_pictures, void *d_scratch, int64_t scratch_bytes, void *stream)
+                uint16_t *d_pictures, void *d_scratch, int64_t scratch_bytes, int32_t *d_status, void *stream)
 {
     DevParams P;
     int st = make_dev_params(p, &P);
     if (st) return st;
-    if (!coeff16_transform_ok(P) || !d_coeffs16) return VC2B_E_UNSUPPORTED;
+    if (!coeff16_transform_ok(P)) return VC2B_E_UNSUPPORTED;
+    if (!d_coeffs16 || !d_status) return VC2B_E_BAD_PARAMS;
     if ((reinterpret_cast<uintptr_t>(d_coeffs) & 15) || (reinterpret_cast<uintptr_t>(d_coeffs16) & 15) ||
         (reinterpret_cast<uintptr_t>(d_scratch) & 15))
         return VC2B_E_BAD_PARAMS;
     if (npictures <= 0) return 0;
     ScratchPlan sp;
     plan_scratch(P, 0, 3, &sp);
-    const long long per_pic = (sp.size_a + sp.size_b) * (long long)sizeof(int32_t);
+    const long long per_pic = (sp.size_a + sp.size_b) * (long long)sizeof(int16_t);  // int16 intermediate bands
     int group = per_pic > 0 ? (int)(scratch_bytes / per_pic) : npictures;
     if (group < 1) return VC2B_E_SCRATCH_TOO_SMALL;
     if (group > npictures) group = npictures;
@@ -660,7 +672,7 @@ int vc2b_idwt16(const vc2b_params *p, const int32_t *d_coeffs, const int16_t *d_
         const int n = (npictures - i < group) ? npictures - i : group;
         st = run_idwt(P, 0, 3, d_coeffs + (long long)i * P.pic_coeffs, d_coeffs16 + (long long)i * P.pic_coeffs,
                       P.pic_coeffs, n, d_pictures + (long long)i * P.pic_samples, nullptr, (int32_t *)d_scratch, sp,
-                      (cudaStream_t)stream);
+                      d_status + 4LL * i, (cudaStream_t)stream);
         if (st) return st;
     }
     return 0;
@@ -678,7 +690,7 @@ int vc2b_idwt_raw(const vc2b_params *p, int comp, const int32_t *d_coeffs, int32
     if ((sp.size_a + sp.size_b) * (long long)sizeof(int32_t) > scratch_bytes) return VC2B_E_SCRATCH_TOO_SMALL;
     // d_coeffs points at the component's own coefficients
     return run_idwt(P, comp, comp + 1, d_coeffs - P.comp_off[comp], nullptr, 0, 1, nullptr, d_out,
-                    (int32_t *)d_scratch, sp, (cudaStream_t)stream);
+                    (int32_t *)d_scratch, sp, nullptr, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -51,7 +51,10 @@ struct Strip8Ctx {
     int32_t *out;
     int W2;
     uint64_t pol_ll, pol_hb, pol_out;  // L2 eviction policies of the LL input, the high-pass inputs and the output
+    mutable int lo16, hi16;            // kModeOut16: smallest / largest value this lane stored
 };
+
+enum { kModeHb16 = 1, kModeLl16 = 2, kModeOut16 = 4 };
 
 struct RawPair {
     int ll[kWideNP], b0[kWideNP], b1[kWideNP], b2[kWideNP];
@@ -80,17 +83,21 @@ __device__ __forceinline__ void half_to_array(const WideVec *slot, int (&a)[kWid
 }
 
 // issue the asynchronous copy of pair m (one commit group per pair); NS = number of stage slots.
-// HB16: the high-pass bands are int16 (the coefficient plane written by vc2b_unpack16); X.b0..b2 then
-// point at int16 rows and a vector is NP * 2 bytes.
-template <int NS, bool HB16>
+// MODE (the int16 planes of vc2b_idwt16): kModeHb16 -- the high-pass bands are int16 (the coefficient plane
+// written by vc2b_unpack16), X.b0..b2 point at int16 rows and a vector is NP * 2 bytes; kModeLl16 -- so is the
+// LL input (the previous level's output); kModeOut16 -- this level writes its output as int16.
+template <int NS, int MODE>
 __device__ __forceinline__ void stage_pair8(const Strip8Ctx &X, WideVec *smem, int m)
 {
     const int sy = min(max(m, 0), X.h - 1);
     const int idx = sy * X.wq + X.jqc;
     WideVec *st = smem + ((((m % NS) + NS) % NS) * 4) * 32 + X.lane;
-    if constexpr (HB16) {
-        constexpr int HB = kWideNP * 2;  // bytes per high-pass vector
-        cp_async_vec(st, X.ll + idx);
+    if constexpr ((MODE & kModeHb16) != 0) {
+        constexpr int HB = kWideNP * 2;  // bytes per int16 vector
+        if constexpr ((MODE & kModeLl16) != 0)
+            cp_async_half(st, reinterpret_cast<const char *>(X.ll) + (long long)idx * HB);
+        else
+            cp_async_vec(st, X.ll + idx);
         cp_async_half(st + 32, reinterpret_cast<const char *>(X.b0) + (long long)idx * HB);
         cp_async_half(st + 64, reinterpret_cast<const char *>(X.b1) + (long long)idx * HB);
         cp_async_half(st + 96, reinterpret_cast<const char *>(X.b2) + (long long)idx * HB);
@@ -110,15 +117,15 @@ __device__ __forceinline__ void stage_pair8(const Strip8Ctx &X, WideVec *smem, i
 
 // At step t the even row of pair t - E0 and the odd row of pair t - E1 enter the register ring.
 // The youngest of them was issued LOOK - 1 commit groups before the newest group in flight.
-template <int NS, int E0, int E1, bool HB16, int LOOK = 4>
+template <int NS, int E0, int E1, int MODE, int LOOK = 4>
 __device__ __forceinline__ void load_pair8(const Strip8Ctx &X, const WideVec *smem, int t, RawPair &r)
 {
     asm volatile("cp.async.wait_group %0;" ::"n"(LOOK - 1) : "memory");
     const int me = t - E0, mo = t - E1;
     const WideVec *se = smem + ((((me % NS) + NS) % NS) * 4) * 32 + X.lane;
     const WideVec *so = smem + ((((mo % NS) + NS) % NS) * 4) * 32 + X.lane;
-    vec_to_array(se[0], r.ll);
-    if constexpr (HB16) {
+    if constexpr ((MODE & kModeLl16) != 0) half_to_array(se, r.ll); else vec_to_array(se[0], r.ll);
+    if constexpr ((MODE & kModeHb16) != 0) {
         half_to_array(se + 32, r.b0);
         half_to_array(so + 64, r.b1);
         half_to_array(so + 96, r.b2);
@@ -143,7 +150,7 @@ __device__ __forceinline__ void put_pair8(PairRing<RING, kWideNC> &R, int slot_e
     }
 }
 
-template <int FH, bool FINAL>
+template <int FH, bool FINAL, bool OUT16 = false>
 __device__ __forceinline__ void finish_row8(const Strip8Ctx &X, int gy, int (&E)[kWideNP], int (&O)[kWideNP])
 {
     constexpr int NP = kWideNP, NC = kWideNC;
@@ -168,6 +175,19 @@ __device__ __forceinline__ void finish_row8(const Strip8Ctx &X, int gy, int (&E)
                 }
             }
         }
+    } else if (OUT16) {
+        if (X.lane_ok) {  // int16 output (vc2b_idwt16): one 16-byte store per row, range tracked per lane
+            uint32_t pk[NP];
+#pragma unroll
+            for (int i = 0; i < NP; i++) {
+                const int v0 = (E[i] + X.rnd) >> X.shift, v1 = (O[i] + X.rnd) >> X.shift;
+                X.lo16 = min(X.lo16, min(v0, v1));
+                X.hi16 = max(X.hi16, max(v0, v1));
+                pk[i] = ((uint32_t)v0 & 0xffffu) | ((uint32_t)v1 << 16);
+            }
+            int16_t *d = reinterpret_cast<int16_t *>(X.out) + (long long)gy * X.W2 + NC * X.jq;
+            st_hint(d, array_to_uvec(pk), X.pol_out);
+        }
     } else {
         if (X.lane_ok) {
             int lo[NP], hi[NP];  // interleave E/O back into column order
@@ -185,7 +205,7 @@ __device__ __forceinline__ void finish_row8(const Strip8Ctx &X, int gy, int (&E)
     }
 }
 
-template <int FV, int FH, bool FINAL, int U, bool HB16, int LOOK = 4>
+template <int FV, int FH, bool FINAL, int U, int MODE, int LOOK = 4>
 __device__ __forceinline__ void strip8_step_fast(PairRing<Strip8Cfg<FV, FH>::RING, kWideNC> &R, const Strip8Ctx &X,
                                                  WideVec *smem, int t, int K0, int K1)
 {
@@ -194,11 +214,11 @@ __device__ __forceinline__ void strip8_step_fast(PairRing<Strip8Cfg<FV, FH>::RIN
     constexpr int E0 = C::P.entry[0], E1 = C::P.entry[1], NS = LOOK + C::EMAX;
     {
         RawPair r;
-        load_pair8<NS, E0, E1, HB16, LOOK>(X, smem, t, r);
+        load_pair8<NS, E0, E1, MODE, LOOK>(X, smem, t, r);
         put_pair8<RING>(R, (U - E0) & M, (U - E1) & M, r);
     }
     vstep_fast<FV, U, RING, kWideNC>(R);
-    stage_pair8<NS, HB16>(X, smem, t - C::EMAX + NS);  // the slot of pair t - EMAX is free again
+    stage_pair8<NS, MODE>(X, smem, t - C::EMAX + NS);  // the slot of pair t - EMAX is free again
     const int kf = t - C::P.maxlag;
     if (kf >= K0 && kf < K1) {
         constexpr int sl = (U - C::P.maxlag) & M;
@@ -207,21 +227,21 @@ __device__ __forceinline__ void strip8_step_fast(PairRing<Strip8Cfg<FV, FH>::RIN
             int E[kWideNP], O[kWideNP];
 #pragma unroll
             for (int i = 0; i < kWideNP; i++) { E[i] = R.v[par][2 * i][sl]; O[i] = R.v[par][2 * i + 1][sl]; }
-            finish_row8<FH, FINAL>(X, 2 * kf + par, E, O);
+            finish_row8<FH, FINAL, (MODE & kModeOut16) != 0>(X, 2 * kf + par, E, O);
         }
     }
 }
 
-template <int FV, int FH, bool FINAL, int U, bool HB16, int LOOK = 4>
+template <int FV, int FH, bool FINAL, int U, int MODE, int LOOK = 4>
 __device__ __forceinline__ void strip8_block_fast(PairRing<Strip8Cfg<FV, FH>::RING, kWideNC> &R, const Strip8Ctx &X,
                                                   WideVec *smem, int t0, int K0, int K1)
 {
-    strip8_step_fast<FV, FH, FINAL, U, HB16, LOOK>(R, X, smem, t0 + U, K0, K1);
+    strip8_step_fast<FV, FH, FINAL, U, MODE, LOOK>(R, X, smem, t0 + U, K0, K1);
     if constexpr (U + 1 < Strip8Cfg<FV, FH>::RING)
-        strip8_block_fast<FV, FH, FINAL, U + 1, HB16, LOOK>(R, X, smem, t0, K0, K1);
+        strip8_block_fast<FV, FH, FINAL, U + 1, MODE, LOOK>(R, X, smem, t0, K0, K1);
 }
 
-template <int FV, int FH, bool FINAL, bool HB16, int LOOK = 4>
+template <int FV, int FH, bool FINAL, int MODE, int LOOK = 4>
 __device__ __forceinline__ void strip8_step_slow(PairRing<Strip8Cfg<FV, FH>::RING, kWideNC> &R, const Strip8Ctx &X,
                                                  WideVec *smem, int t, int ks, int last, int K0, int K1)
 {
@@ -229,7 +249,7 @@ __device__ __forceinline__ void strip8_step_slow(PairRing<Strip8Cfg<FV, FH>::RIN
     constexpr int RING = C::RING, M = RING - 1;
     constexpr int E0 = C::P.entry[0], E1 = C::P.entry[1], NS = LOOK + C::EMAX;
     RawPair r;
-    load_pair8<NS, E0, E1, HB16, LOOK>(X, smem, t, r);
+    load_pair8<NS, E0, E1, MODE, LOOK>(X, smem, t, r);
     const int le = (t - E0 - ks) & M, lo = (t - E1 - ks) & M;
 #pragma unroll
     for (int i = 0; i < RING; i++) {
@@ -240,7 +260,7 @@ __device__ __forceinline__ void strip8_step_slow(PairRing<Strip8Cfg<FV, FH>::RIN
         }
     }
     vstep_slow<FV, RING, kWideNC>(R, t, ks, last);
-    stage_pair8<NS, HB16>(X, smem, t - C::EMAX + NS);
+    stage_pair8<NS, MODE>(X, smem, t - C::EMAX + NS);
     const int kf = t - C::P.maxlag;
     if (kf >= K0 && kf < K1) {
         const int sl = (kf - ks) & M;
@@ -252,12 +272,12 @@ __device__ __forceinline__ void strip8_step_slow(PairRing<Strip8Cfg<FV, FH>::RIN
                 E[i] = ring_get_dyn<RING>(R.v[par][2 * i], sl);
                 O[i] = ring_get_dyn<RING>(R.v[par][2 * i + 1], sl);
             }
-            finish_row8<FH, FINAL>(X, 2 * kf + par, E, O);
+            finish_row8<FH, FINAL, (MODE & kModeOut16) != 0>(X, 2 * kf + par, E, O);
         }
     }
 }
 
-template <int FV, int FH, bool FINAL, int STEPS, bool HB16>
+template <int FV, int FH, bool FINAL, int STEPS, int MODE>
 __device__ __forceinline__ void run_strip8(const Strip8Ctx &X, WideVec *smem, int ty)
 {
     using C = Strip8Cfg<FV, FH, STEPS>;
@@ -271,19 +291,19 @@ __device__ __forceinline__ void run_strip8(const Strip8Ctx &X, WideVec *smem, in
     const int K0 = ty * C::RSP, K1 = min(K0 + C::RSP, X.h);
     const int ks = K0 - C::P.warm;
 #pragma unroll
-    for (int u = 0; u < C::STAGES; u++) stage_pair8<C::STAGES, HB16>(X, smem, ks - C::EMAX + u);
+    for (int u = 0; u < C::STAGES; u++) stage_pair8<C::STAGES, MODE>(X, smem, ks - C::EMAX + u);
     const int t_end = K1 - 1 + C::P.maxlag;
     for (int t0 = ks; t0 <= t_end; t0 += RING) {
         if (t0 >= C::P.back && t0 + RING - 1 <= last) {
-            strip8_block_fast<FV, FH, FINAL, 0, HB16>(R, X, smem, t0, K0, K1);
+            strip8_block_fast<FV, FH, FINAL, 0, MODE>(R, X, smem, t0, K0, K1);
         } else {
 #pragma unroll 1
-            for (int u = 0; u < RING; u++) strip8_step_slow<FV, FH, FINAL, HB16>(R, X, smem, t0 + u, ks, last, K0, K1);
+            for (int u = 0; u < RING; u++) strip8_step_slow<FV, FH, FINAL, MODE>(R, X, smem, t0 + u, ks, last, K0, K1);
         }
     }
 }
 
-template <int FV, int FH, int STEPS, bool HB16>
+template <int FV, int FH, int STEPS, int MODE>
 __global__ void __launch_bounds__(32)
 idwt_stream8_kernel(LevelArgs A)
 {
@@ -305,8 +325,11 @@ idwt_stream8_kernel(LevelArgs A)
     X.lane_lo = C::HLQ - tx * (C::WOUT / NC);
     X.lane_hi = X.lane_lo + X.wq - 1;
     X.lane_ok = (X.lane >= C::HLQ) && (X.lane < 32 - C::HLQ) && (X.jq >= 0) && (X.jq < X.wq);
-    X.ll = reinterpret_cast<const WideVec *>(A.ll[c] + (long long)pic * A.ll_pic_stride[c]);
-    if constexpr (HB16) {  // A.hb* address int16 rows (LevelArgs::hb16)
+    if constexpr ((MODE & kModeLl16) != 0)
+        X.ll = reinterpret_cast<const WideVec *>(reinterpret_cast<const int16_t *>(A.ll[c]) + (long long)pic * A.ll_pic_stride[c]);
+    else
+        X.ll = reinterpret_cast<const WideVec *>(A.ll[c] + (long long)pic * A.ll_pic_stride[c]);
+    if constexpr ((MODE & kModeHb16) != 0) {  // A.hb* address int16 rows
         const int16_t *h0 = reinterpret_cast<const int16_t *>(A.hb[c][0]), *h1 = reinterpret_cast<const int16_t *>(A.hb[c][1]);
         const int16_t *h2 = reinterpret_cast<const int16_t *>(A.hb[c][2]);
         X.b0 = reinterpret_cast<const WideVec *>(h0 + (long long)pic * A.hb_pic_stride);
@@ -326,14 +349,28 @@ idwt_stream8_kernel(LevelArgs A)
     X.cw = A.crop_w[c];
     X.ch = A.crop_h[c];
     X.vec_store = ((X.cw % NC) == 0) && ((reinterpret_cast<uintptr_t>(X.pic) % (2 * NC)) == 0);
-    X.out = A.out[c] + (long long)pic * A.out_pic_stride[c];
+    if constexpr ((MODE & kModeOut16) != 0)
+        X.out = reinterpret_cast<int32_t *>(reinterpret_cast<int16_t *>(A.out[c]) + (long long)pic * A.out_pic_stride[c]);
+    else
+        X.out = A.out[c] + (long long)pic * A.out_pic_stride[c];
+    X.lo16 = X.hi16 = 0;
     X.W2 = 2 * A.w[c];
     X.hedge = (X.lane_lo > 0) || (X.lane_hi < 31);
     X.ld_hints = A.hint_loads != 0;
     X.pol_ll = l2_policy(A.hint_ll);
     X.pol_hb = l2_policy(A.hint_hb);
     X.pol_out = l2_policy(A.hint_out);
-    if (A.final_u16) run_strip8<FV, FH, true, STEPS, HB16>(X, smem, ty); else run_strip8<FV, FH, false, STEPS, HB16>(X, smem, ty);
+    if constexpr ((MODE & kModeOut16) != 0) {
+        run_strip8<FV, FH, false, STEPS, MODE>(X, smem, ty);
+        // a value outside int16: the picture has to be decoded again through the int32 planes (never over a
+        // status the unpack set)
+        if (__any_sync(0xffffffffu, X.hi16 > 32767 || X.lo16 < -32768) && threadIdx.x == 0)
+            atomicCAS(A.status + 4 * (long long)pic, VC2B_ST_OK, VC2B_ST_COEFF16_RANGE);
+    } else if constexpr (MODE != 0) {
+        run_strip8<FV, FH, true, STEPS, MODE>(X, smem, ty);   // int16 inputs: only vc2b_idwt16's last level
+    } else {
+        if (A.final_u16) run_strip8<FV, FH, true, STEPS, MODE>(X, smem, ty); else run_strip8<FV, FH, false, STEPS, MODE>(X, smem, ty);
+    }
     asm volatile("cp.async.wait_group 0;" ::: "memory");  // drain look-ahead copies before exit
 }
 
@@ -342,16 +379,17 @@ idwt_stream8_kernel(LevelArgs A)
 static bool level_is_wide_ok(const LevelArgs &A, int npic)
 {
     constexpr int NP = kWideNP;
-    constexpr uintptr_t amask = 4 * NP - 1;
+    constexpr uintptr_t amask = 4 * NP - 1;  // int32 vectors; int16 vectors need half of it
+    const uintptr_t m_ll = A.ll16 ? amask >> 1 : amask, m_hb = A.hb16 ? amask >> 1 : amask;
     for (int c = 0; c < A.ncomp; c++) {
         if (A.w[c] % NP) return false;
-        if (reinterpret_cast<uintptr_t>(A.ll[c]) & amask) return false;
+        if (reinterpret_cast<uintptr_t>(A.ll[c]) & m_ll) return false;
         if (npic > 1 && (A.ll_pic_stride[c] % NP)) return false;
         for (int k = 0; k < 3; k++)
-            if (reinterpret_cast<uintptr_t>(A.hb[c][k]) & (A.hb16 ? amask >> 1 : amask)) return false;
+            if (reinterpret_cast<uintptr_t>(A.hb[c][k]) & m_hb) return false;
         if (!A.final_u16) {
-            if (reinterpret_cast<uintptr_t>(A.out[c]) & amask) return false;
-            if (npic > 1 && (A.out_pic_stride[c] % NP)) return false;
+            if (reinterpret_cast<uintptr_t>(A.out[c]) & amask) return false;  // 16-byte stores in both modes
+            if (npic > 1 && (A.out_pic_stride[c] % (A.out16 ? 2 * NP : NP))) return false;
         }
     }
     if (npic > 1 && (A.hb_pic_stride % NP)) return false;  // elements: int32 or int16 (hb16)
@@ -372,10 +410,17 @@ static int launch_wide_steps(LevelArgs A, int npic, cudaStream_t s)
         maxtiles = max(maxtiles, A.tiles_x[c] * A.tiles_y[c]);
     }
     dim3 grid(maxtiles, A.ncomp, npic);
-    if (A.hb16)
-        idwt_stream8_kernel<FV, FH, STEPS, true><<<grid, 32, 0, s>>>(A);
-    else
-        idwt_stream8_kernel<FV, FH, STEPS, false><<<grid, 32, 0, s>>>(A);
+    const int mode = (A.hb16 ? kModeHb16 : 0) | (A.ll16 ? kModeLl16 : 0) | (A.out16 ? kModeOut16 : 0);
+    switch (mode) {
+    case 0: idwt_stream8_kernel<FV, FH, STEPS, 0><<<grid, 32, 0, s>>>(A); break;
+    case kModeHb16: idwt_stream8_kernel<FV, FH, STEPS, kModeHb16><<<grid, 32, 0, s>>>(A); break;
+    case kModeHb16 | kModeLl16: idwt_stream8_kernel<FV, FH, STEPS, kModeHb16 | kModeLl16><<<grid, 32, 0, s>>>(A); break;
+    case kModeHb16 | kModeOut16: idwt_stream8_kernel<FV, FH, STEPS, kModeHb16 | kModeOut16><<<grid, 32, 0, s>>>(A); break;
+    case kModeHb16 | kModeLl16 | kModeOut16:
+        idwt_stream8_kernel<FV, FH, STEPS, kModeHb16 | kModeLl16 | kModeOut16><<<grid, 32, 0, s>>>(A);
+        break;
+    default: return VC2B_E_UNSUPPORTED;
+    }
     VC2B_CHECK_LAUNCH();
     return 0;
 }

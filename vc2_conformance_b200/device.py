@@ -218,7 +218,7 @@ class BatchCodec(object):
                 capi.check("vc2b_idwt16",
                            L.vc2b_idwt16(C.byref(p), _ptr(coeffs), _ptr(self.coeffs16[first * g.picture_coeffs:]), n,
                                          _ptr(pics), _ptr(self.scratch), self.scratch.numel(),
-                                         self._stream_ptr(stream)))
+                                         _ptr(self.status[first * 4:]), self._stream_ptr(stream)))
             else:
                 capi.check("vc2b_idwt",
                            L.vc2b_idwt(C.byref(p), _ptr(coeffs), n, _ptr(pics), _ptr(self.scratch),
