@@ -82,6 +82,18 @@ __device__ __forceinline__ void half_to_array(const WideVec *slot, int (&a)[kWid
     }
 }
 
+// a 16-byte slot holding two vectors of NP int16 coefficients each, widened to int32
+__device__ __forceinline__ void int16x8_to_arrays(const int4 &v, int (&a)[4], int (&b)[4])
+{
+    a[0] = (int)(short)(v.x & 0xffff); a[1] = v.x >> 16; a[2] = (int)(short)(v.y & 0xffff); a[3] = v.y >> 16;
+    b[0] = (int)(short)(v.z & 0xffff); b[1] = v.z >> 16; b[2] = (int)(short)(v.w & 0xffff); b[3] = v.w >> 16;
+}
+__device__ __forceinline__ void int16x8_to_arrays(const int2 &v, int (&a)[2], int (&b)[2])
+{
+    a[0] = (int)(short)(v.x & 0xffff); a[1] = v.x >> 16;
+    b[0] = (int)(short)(v.y & 0xffff); b[1] = v.y >> 16;
+}
+
 // issue the asynchronous copy of pair m (one commit group per pair); NS = number of stage slots.
 // MODE (the int16 planes of vc2b_idwt16): kModeHb16 -- the high-pass bands are int16 (the coefficient plane
 // written by vc2b_unpack16), X.b0..b2 point at int16 rows and a vector is NP * 2 bytes; kModeLl16 -- so is the
@@ -91,13 +103,19 @@ __device__ __forceinline__ void stage_pair8(const Strip8Ctx &X, WideVec *smem, i
 {
     const int sy = min(max(m, 0), X.h - 1);
     const int idx = sy * X.wq + X.jqc;
-    WideVec *st = smem + ((((m % NS) + NS) % NS) * 4) * 32 + X.lane;
-    if constexpr ((MODE & kModeHb16) != 0) {
+    constexpr int SLOTS = (MODE & kModeLl16) ? 2 : 4;  // vectors per lane and stage
+    WideVec *st = smem + ((((m % NS) + NS) % NS) * SLOTS) * 32 + X.lane;
+    if constexpr ((MODE & kModeLl16) != 0) {
+        // all four inputs are int16: two 16-byte slots per lane -- {LL, HL} feed the even row, {LH, HH} the odd one
         constexpr int HB = kWideNP * 2;  // bytes per int16 vector
-        if constexpr ((MODE & kModeLl16) != 0)
-            cp_async_half(st, reinterpret_cast<const char *>(X.ll) + (long long)idx * HB);
-        else
-            cp_async_vec(st, X.ll + idx);
+        char *lo = reinterpret_cast<char *>(st), *hi = reinterpret_cast<char *>(st + 32);
+        cp_async_half(reinterpret_cast<WideVec *>(lo), reinterpret_cast<const char *>(X.ll) + (long long)idx * HB);
+        cp_async_half(reinterpret_cast<WideVec *>(lo + HB), reinterpret_cast<const char *>(X.b0) + (long long)idx * HB);
+        cp_async_half(reinterpret_cast<WideVec *>(hi), reinterpret_cast<const char *>(X.b1) + (long long)idx * HB);
+        cp_async_half(reinterpret_cast<WideVec *>(hi + HB), reinterpret_cast<const char *>(X.b2) + (long long)idx * HB);
+    } else if constexpr ((MODE & kModeHb16) != 0) {
+        constexpr int HB = kWideNP * 2;
+        cp_async_vec(st, X.ll + idx);
         cp_async_half(st + 32, reinterpret_cast<const char *>(X.b0) + (long long)idx * HB);
         cp_async_half(st + 64, reinterpret_cast<const char *>(X.b1) + (long long)idx * HB);
         cp_async_half(st + 96, reinterpret_cast<const char *>(X.b2) + (long long)idx * HB);
@@ -122,17 +140,23 @@ __device__ __forceinline__ void load_pair8(const Strip8Ctx &X, const WideVec *sm
 {
     asm volatile("cp.async.wait_group %0;" ::"n"(LOOK - 1) : "memory");
     const int me = t - E0, mo = t - E1;
-    const WideVec *se = smem + ((((me % NS) + NS) % NS) * 4) * 32 + X.lane;
-    const WideVec *so = smem + ((((mo % NS) + NS) % NS) * 4) * 32 + X.lane;
-    if constexpr ((MODE & kModeLl16) != 0) half_to_array(se, r.ll); else vec_to_array(se[0], r.ll);
-    if constexpr ((MODE & kModeHb16) != 0) {
-        half_to_array(se + 32, r.b0);
-        half_to_array(so + 64, r.b1);
-        half_to_array(so + 96, r.b2);
+    constexpr int SLOTS = (MODE & kModeLl16) ? 2 : 4;
+    const WideVec *se = smem + ((((me % NS) + NS) % NS) * SLOTS) * 32 + X.lane;
+    const WideVec *so = smem + ((((mo % NS) + NS) % NS) * SLOTS) * 32 + X.lane;
+    if constexpr ((MODE & kModeLl16) != 0) {
+        int16x8_to_arrays(se[0], r.ll, r.b0);   // one 16-byte shared load per row
+        int16x8_to_arrays(so[32], r.b1, r.b2);
     } else {
-        vec_to_array(se[32], r.b0);
-        vec_to_array(so[64], r.b1);
-        vec_to_array(so[96], r.b2);
+        vec_to_array(se[0], r.ll);
+        if constexpr ((MODE & kModeHb16) != 0) {
+            half_to_array(se + 32, r.b0);
+            half_to_array(so + 64, r.b1);
+            half_to_array(so + 96, r.b2);
+        } else {
+            vec_to_array(se[32], r.b0);
+            vec_to_array(so[64], r.b1);
+            vec_to_array(so[96], r.b2);
+        }
     }
 }
 
@@ -304,12 +328,12 @@ __device__ __forceinline__ void run_strip8(const Strip8Ctx &X, WideVec *smem, in
 }
 
 template <int FV, int FH, int STEPS, int MODE>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(32, (MODE & kModeHb16) ? 16 : 1)
 idwt_stream8_kernel(LevelArgs A)
 {
     using C = Strip8Cfg<FV, FH, STEPS>;
     constexpr int NP = kWideNP, NC = kWideNC;
-    __shared__ __align__(16) WideVec smem[C::STAGES * 4 * 32];
+    __shared__ __align__(16) WideVec smem[C::STAGES * ((MODE & kModeLl16) ? 2 : 4) * 32];
     const int c = blockIdx.y;
     const int pic = blockIdx.z;
     const int tx = blockIdx.x % A.tiles_x[c];
