@@ -43,7 +43,7 @@ struct Strip8Ctx {
     const WideVec *ll, *b0, *b1, *b2;  // row-major, w/NP vectors per row
     int wq, h, jq, jqc, lane, lane_lo, lane_hi;
     bool lane_ok, hedge, ld_hints;
-    int shift, cadd, vmax;             // final: v = clamp((x + cadd) >> shift, 0, vmax)
+    int shift, cadd, vmax, vmaxs;      // final: v = clamp((x + cadd) >> shift, 0, vmax); vmaxs = (vmax << shift) | (2^shift - 1)
     int rnd;
     uint16_t *pic;
     int cw, ch;
@@ -55,6 +55,9 @@ struct Strip8Ctx {
 };
 
 enum { kModeHb16 = 1, kModeLl16 = 2, kModeOut16 = 4 };
+#ifndef VC2B_IDWT16_MINB
+#define VC2B_IDWT16_MINB 16   // resident warps per SM the all-int16 levels are compiled for
+#endif
 
 struct RawPair {
     int ll[kWideNP], b0[kWideNP], b1[kWideNP], b2[kWideNP];
@@ -184,9 +187,11 @@ __device__ __forceinline__ void finish_row8(const Strip8Ctx &X, int gy, int (&E)
             uint32_t pk[NP];
 #pragma unroll
             for (int i = 0; i < NP; i++) {
-                const int v0 = min(max((E[i] + X.cadd) >> X.shift, 0), X.vmax);
-                const int v1 = min(max((O[i] + X.cadd) >> X.shift, 0), X.vmax);
-                pk[i] = (uint32_t)v0 | ((uint32_t)v1 << 16);
+                // clamp((x + cadd) >> s, 0, vmax) == clamp(x + cadd, 0, (vmax << s) | (2^s - 1)) >> s: one
+                // add-min-relu instruction (VIADDMNMX.RELU) and a shift per sample, one PRMT per pair
+                const int v0 = __viaddmin_s32_relu(E[i], X.cadd, X.vmaxs) >> X.shift;
+                const int v1 = __viaddmin_s32_relu(O[i], X.cadd, X.vmaxs) >> X.shift;
+                pk[i] = __byte_perm((uint32_t)v0, (uint32_t)v1, 0x5410);
             }
             uint16_t *d = X.pic + (long long)gy * X.cw + NC * X.jq;
             if (X.vec_store && NC * X.jq + NC <= X.cw) {
@@ -328,7 +333,7 @@ __device__ __forceinline__ void run_strip8(const Strip8Ctx &X, WideVec *smem, in
 }
 
 template <int FV, int FH, int STEPS, int MODE>
-__global__ void __launch_bounds__(32, (MODE & kModeHb16) ? 16 : 1)
+__global__ void __launch_bounds__(32, (MODE & kModeLl16) ? VC2B_IDWT16_MINB : ((MODE & kModeHb16) ? 16 : 1))
 idwt_stream8_kernel(LevelArgs A)
 {
     using C = Strip8Cfg<FV, FH, STEPS>;
@@ -369,6 +374,7 @@ idwt_stream8_kernel(LevelArgs A)
     const int half = 1 << (A.depth[c] - 1);
     X.cadd = X.rnd + (half << A.shift);   // ((x + rnd) >> s) + half == (x + rnd + (half << s)) >> s
     X.vmax = 2 * half - 1;
+    X.vmaxs = (X.vmax << A.shift) | ((1 << A.shift) - 1);
     X.pic = A.pic[c] + (long long)pic * A.pic_pic_stride;
     X.cw = A.crop_w[c];
     X.ch = A.crop_h[c];

@@ -219,6 +219,7 @@ idwt_ring_kernel(LevelArgs A)
     const int half = 1 << (A.depth[c] - 1);
     X.cadd = X.rnd + (half << A.shift);
     X.vmax = 2 * half - 1;
+    X.vmaxs = (X.vmax << A.shift) | ((1 << A.shift) - 1);
     X.pic = A.pic[c] + (long long)pic * A.pic_pic_stride;
     X.cw = A.crop_w[c];
     X.ch = A.crop_h[c];
