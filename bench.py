@@ -75,14 +75,15 @@ WORKLOADS = {
 }
 
 
-# DRAM traffic per picture (dram__bytes_read.sum + dram__bytes_write.sum) from `ncu --set full`
-# captures of these kernels on this workload; the summaries are committed under profiles/.
-NCU_TRAFFIC_PER_PICTURE = {
-    "cfg2": {
-        "unpack": (71.6e6, "profiles/r1_v9_unpack_lanes_ncu_full_raw.csv (unpack_lanes_kernel, 32 pictures: 0.215 GB read + 2.077 GB written)"),
-        "idwt": (144.0e6, "profiles/r1_v4_idwt_levels_ncu.csv (4 idwt_stream8_kernel launches, 16 pictures)"),
-    },
-}
+# DRAM traffic per picture (dram__bytes_read.sum + dram__bytes_write.sum) from `ncu --set full` captures of
+# these kernels on this workload: profiles/traffic.json names the committed summary each figure comes from.
+def ncu_traffic(workload, plane, stage):
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            e = json.load(f)[workload][plane][stage]
+        return float(e["bytes_per_picture"]), e["source"]
+    except (OSError, KeyError, ValueError):
+        return None, None
 
 
 def parse_args():
@@ -695,10 +696,11 @@ def run_decode(args):
                  "kernels": "%d transform levels (last fused with crop+clip+offset)" % (p.dwt_depth + p.dwt_depth_ho)},
     }
     dom = "unpack" if ms_unpack >= ms_idwt else "idwt"
-    traffic, traffic_src = None, None
-    if args.workload in NCU_TRAFFIC_PER_PICTURE and dom in NCU_TRAFFIC_PER_PICTURE[args.workload]:
-        per_pic, traffic_src = NCU_TRAFFIC_PER_PICTURE[args.workload][dom]
-        traffic = per_pic * NP  # per launch of the stage, like `achieved`
+    per_pic, traffic_src = ncu_traffic(args.workload, "int16" if codec.coeff16 else "int32", dom)
+    traffic = per_pic * NP if per_pic else None  # per launch of the stage, like `achieved`
+    for st_name in stages:
+        pp, _src = ncu_traffic(args.workload, "int16" if codec.coeff16 else "int32", st_name)
+        stages[st_name]["dram_traffic_per_picture"] = pp
     roofline = {"bound": "hbm", "stage": dom, "achieved": stages[dom]["achieved"], "peak": peak, "unit": "GB/s",
                 "frac": stages[dom]["frac"], "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_bytes": stages[dom]["algorithmic_bytes_per_picture"] * NP, "peak_source": peak_src}
