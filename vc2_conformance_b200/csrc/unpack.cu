@@ -1085,8 +1085,9 @@ static int unpack_impl(const vc2b_params *p, const uint8_t *d_data, const int64_
     if (lanes) {
         const long long tasks = (long long)npictures * ((P.slices_x * P.slices_y + 31) / 32);
         long long nblk = (tasks + kLaneWarps - 1) / kLaneWarps;
-        // persistent: two CTAs of twelve warps per SM (the two-code table is 16 KB per CTA)
-        const long long max_blocks = 148LL * 2;
+        // persistent: one CTA of 24 warps per SM (222 KB of shared memory: tables + a tile, a rectangle table and
+        // a bitstream FIFO per warp)
+        const long long max_blocks = 148LL;
         if (nblk > max_blocks) nblk = max_blocks;
         const void *fn = P.is_ld ? (d_coeffs16 ? (const void *)unpack_lanes_kernel<true, true>
                                                : (const void *)unpack_lanes_kernel<true, false>)

@@ -22,7 +22,7 @@
 
 namespace vc2b {
 
-constexpr int kLaneWarps = 12;           // warps per CTA (two CTAs per SM share the tables of LaneBlock)
+constexpr int kLaneWarps = 24;           // warps per CTA: one persistent CTA per SM (the tables of LaneBlock once per SM)
 constexpr int kPairBits = 12;            // window of the two-code look-up table
 constexpr int kPairEntries = 1 << kPairBits;
 constexpr uint32_t kPairMaxQf = (1u << 26) - 1;  // 30 * qf + quant_offset + 2 < 2^31
@@ -30,12 +30,13 @@ constexpr int kLaneBands = 16;           // subbands per component this kernel s
 constexpr int kLaneMaxCoef = 512;        // coefficients per slice component this kernel supports
 constexpr int kLaneBaseStride = kLaneBands + 1;
 constexpr int kLaneChunk = 16;           // codes per lane between two store phases
+constexpr uint32_t kLaneFifoBytes = 128;  // per lane: eight 16-byte pieces of its bitstream
 constexpr int kLaneTS = 34;              // tile row stride: conflict-free for both access patterns
 
 struct __align__(16) LaneWarp {          // per-warp shared memory
     int32_t tile[kLaneChunk * kLaneTS];  // [code of the chunk][slice]
     int32_t base[32 * kLaneBaseStride];  // [slice][band]: offset of the rectangle in the component
-    uint4 stage[32][2];                  // [lane][slot]: the lane's bitstream, 16 bytes per slot (lane_fetch)
+    uint4 stage[32][kLaneFifoBytes / 16];   // [lane][piece]: the lane's bitstream FIFO (lane_top_up / lane_fetch)
 };
 
 struct __align__(16) LaneBlock {                       // per-CTA shared memory
@@ -136,16 +137,15 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
     return v;
 }
 
-// The bitstream of a lane reaches it through shared memory: two lane-private 16-byte slots filled by
-// cp.async, one piece ahead of the one being read.  (Per-lane 4-byte global loads were the largest stall of
-// this kernel -- every load touches 32 different L1 lines and its scoreboard had to be waited for at the
-// top of every group of codes; a cp.async group is waited for four refills after it was issued.)
+// The bitstream of a lane reaches it through shared memory: a lane-private FIFO of eight 16-byte pieces
+// filled by cp.async.  (Per-lane 4-byte global loads were the largest stall of this kernel -- every load
+// touches 32 different L1 lines and its scoreboard had to be waited for at the top of every group of codes.)
 struct LaneReader {
     const uint4 *cp;      // next 16-byte piece of the stream to stage
     uint64_t buf;         // bit buffer, next bit at the top; bits below `avail` are zero
-    uint32_t ahead;       // the word after the buffer (raw), read from the slots one refill early
-    uint32_t slot;        // shared-memory address of the lane's two slots (32 consecutive bytes)
-    uint32_t wo;          // byte offset (0, 4, .. 28) of the next word to read from the slots
+    uint32_t ahead;       // the word after the buffer (raw), read from the FIFO one refill early
+    uint32_t slot;        // shared-memory address of the lane's FIFO (kLaneFifoBytes consecutive bytes)
+    uint32_t rd, wr;      // bytes read from / staged into the FIFO so far (rd in words, wr in pieces)
     int avail;            // valid bits in buf
     int remaining;        // bits of the bounded block at and after the next word to read (<= 0: past its end)
 };
@@ -155,25 +155,36 @@ __device__ __forceinline__ void lane_stage(uint32_t dst, const uint4 *src)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 
-// Every fourth word: the slot just read to its end is free -- stage the piece after the other slot's into it.
-// The group is committed even when it is empty (the block ends before that piece), so that "all groups but
-// the newest" always covers the slot about to be read.
-__device__ __forceinline__ void lane_next_piece(LaneReader &R)
+// Stages pieces while the FIFO has a free slot (the piece being read is not free) and the block goes on.
+// Called once per chunk of codes, after a wait for what the previous call staged: a piece is read at least
+// a chunk after it was requested, so its latency is never waited for, and the refill itself does no staging
+// (the 32 lanes of a warp refill out of phase: anything on that path runs in almost every group of codes).
+__device__ __forceinline__ void lane_top_up(LaneReader &R)
 {
-    if (R.remaining > 128) lane_stage(R.slot + (R.wo ^ 16u), R.cp);
+    while ((int)(R.wr - (R.rd & ~15u)) <= (int)(kLaneFifoBytes - 16) &&
+           R.remaining > max(8 * (int)(R.wr - R.rd), 0)) {
+        lane_stage(R.slot + (R.wr & (kLaneFifoBytes - 1)), R.cp);
+        R.cp++;
+        R.wr += 16;
+    }
     asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 1;" ::: "memory");
-    R.cp++;
+}
+
+__device__ __forceinline__ void lane_chunk_start(LaneReader &R)
+{
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    lane_top_up(R);
 }
 
 // Takes the next word of the block into `ahead`.  Past the end of the block the word is stale shared memory:
-// lane_ahead_bits turns it into ones.
+// lane_ahead_bits turns it into ones.  No check that the word has arrived: lane_chunk_start leaves at least
+// 98 - 36 = 62 complete bytes ahead of a lane that used 36 bytes in the previous chunk, and a chunk of 32 codes
+// of at most 8 bits (everything but lane_read_long) uses at most 36.
 __device__ __forceinline__ void lane_fetch(LaneReader &R)
 {
-    R.ahead = lds_u32(R.slot + R.wo);
-    R.wo = (R.wo + 4u) & 31u;
+    R.ahead = lds_u32(R.slot + (R.rd & (kLaneFifoBytes - 1)));
+    R.rd += 4;
     R.remaining -= 32;
-    if ((R.wo & 15u) == 0) lane_next_piece(R);
 }
 
 // The word fetched last as 32 bits of the bounded block: ones past its end (decoder/io.py:246-252).
@@ -194,40 +205,45 @@ __device__ __forceinline__ void lane_refill(LaneReader &R)
     }
 }
 
-// `slot`: shared-memory address of the lane's staging slots (LaneWarp::stage).  Reads whole 16-byte pieces:
-// up to 15 bytes before the block and 47 bytes after its start, inside the stream buffer and its slack.
+// The refill of the long-code path, which may use more of the stream than a chunk's budget: everything staged
+// is waited for, and the FIFO is filled up again (and waited for) when less than a chunk's budget is left.
+__device__ __forceinline__ void lane_refill_long(LaneReader &R)
+{
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if ((int)(R.wr - R.rd) < 48 && R.remaining > max(8 * (int)(R.wr - R.rd), 0)) {
+        lane_top_up(R);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    lane_refill(R);
+}
+
+// `slot`: shared-memory address of the lane's FIFO (LaneWarp::stage).  Reads whole 16-byte pieces: up to 15
+// bytes before the block and 15 bytes past its end, inside the stream buffer and its slack.
 __device__ __forceinline__ void lane_reader_init(LaneReader &R, uint32_t slot, const uint8_t *blk, int bit_off,
                                                  long long nbits, bool active)
 {
     const uintptr_t addr = reinterpret_cast<uintptr_t>(blk);
     R.cp = reinterpret_cast<const uint4 *>(addr & ~(uintptr_t)15);
     R.slot = slot;
-    const uint32_t w0 = (uint32_t)(addr & 15);       // byte offset of the first word within its piece
+    const uint32_t wa = (uint32_t)(addr & 12);       // byte offset of the first word within its piece
     const int skip = (int)(addr & 3) * 8 + bit_off;  // <= 31
     long long rem = nbits + skip;
     if (rem > (1LL << 30)) rem = 1LL << 30;          // a slice of this kernel never reads that far
     R.remaining = active ? (int)rem : 0;
-    // the first two pieces are staged together (one load latency); they hold the first three words
-    if (R.remaining > 0) {
-        lane_stage(slot, R.cp);
-        lane_stage(slot + 16, R.cp + 1);
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    R.rd = wa;
+    R.wr = 0;
+    // nothing of the previous block may still be landing in the FIFO; then fill it (most of a block of the
+    // BASELINE streams): one load latency per block
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    R.cp += 2;
-    const uint32_t wa = w0 & 12u;
+    lane_top_up(R);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     uint32_t wd0 = __byte_perm(lds_u32(slot + wa), 0, 0x0123);
     uint32_t wd1 = __byte_perm(lds_u32(slot + wa + 4), 0, 0x0123);
     R.ahead = lds_u32(slot + wa + 8);
     if (R.remaining < 32) wd0 |= 0xffffffffu >> max(R.remaining, 0);
     if (R.remaining < 64) wd1 |= 0xffffffffu >> max(R.remaining - 32, 0);
-    R.wo = wa + 12;          // <= 24: still inside the two slots
+    R.rd = wa + 12;
     R.remaining -= 96;
-    if (R.wo >= 16) {        // the first slot is used up already: stage the third piece into it
-        if (R.remaining > 4 * (int)(64 - 2 * R.wo)) lane_stage(slot, R.cp);   // bits at and after word 8
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        R.cp++;
-    }
     R.buf = (((uint64_t)wd0 << 32) | wd1) << skip;
     R.avail = 64 - skip;
 }
@@ -244,7 +260,7 @@ __device__ __forceinline__ void lane_reader_kill(LaneReader &R)
 // Restores avail >= 32.  Returns false when the value has 32 or more data bits.
 __device__ __forceinline__ bool lane_read_long(LaneReader &R, uint32_t &mag, uint32_t &neg)
 {
-    if (R.avail < 32) lane_refill(R);   // the short-path schedule only guarantees 8 bits
+    if (R.avail < 32) lane_refill_long(R);   // the short-path schedule only guarantees 8 bits
     const uint32_t h2 = (uint32_t)(R.buf >> 32);
     const uint32_t f = h2 & 0xAAAAAAAAu;
     bool ok = true;
@@ -273,14 +289,14 @@ __device__ __forceinline__ bool lane_read_long(LaneReader &R, uint32_t &mag, uin
             nd++;
             R.buf <<= 2;
             R.avail -= 2;
-            if (R.avail < 32) lane_refill(R);
+            if (R.avail < 32) lane_refill_long(R);
         }
         mag = value - 1u;
         neg = (uint32_t)(R.buf >> 62) & 1;
         R.buf <<= 2;
         R.avail -= 2;
     }
-    if (R.avail < 32) lane_refill(R);
+    if (R.avail < 32) lane_refill_long(R);
     return ok;
 }
 
@@ -479,6 +495,7 @@ __device__ __forceinline__ void lanes_block(const DevParams &P, const int comp, 
     const int c = lane & 15, h = lane >> 4;   // store phase: half-warp h takes slice 2k+h, lane c its code c
     for (int j0 = 0; j0 < jmax; j0 += kLaneChunk) {
         // ---- decode: lane = slice, kLaneChunk codes each -------------------------------------------
+        lane_chunk_start(R);
         if (uniform && j0 + kLaneChunk <= refcodes) {
 #pragma unroll 1
             for (int g = 0; g < kLaneChunk / 4; g++) {
@@ -714,44 +731,63 @@ __device__ __forceinline__ void lanes_block16(const DevParams &P, const int comp
         reinterpret_cast<uint32_t *>(t16)[(i) * kLaneTS] = __byte_perm((uint32_t)v1, (uint32_t)v2, 0x5410); \
     }
 
+    // four codes with no band switch among them: two look-ups of two codes each (mark == 1, avail >= 33), or --
+    // when some lane's pair does not fit the window or its quantiser is too large -- four one-code steps
+#define VC2B_LANE_QUAD16()                                                                           \
+    {                                                                                                \
+        const uint32_t ea = lds_u32(plut_addr + (((uint32_t)(R.buf >> 32) >> (32 - kPairBits)) << 2)); \
+        const uint32_t la = ea & 15u;                                                                \
+        const uint64_t bufa = R.buf << la;                                                           \
+        const uint32_t eb = lds_u32(plut_addr + (((uint32_t)(bufa >> 32) >> (32 - kPairBits)) << 2)); \
+        const uint32_t lb = eb & 15u;                                                                \
+        if (__all_sync(0xffffffffu, qfast && la * lb != 0)) {                                        \
+            R.buf = bufa << lb;                                                                      \
+            R.avail -= (int)(la + lb);                                                               \
+            const uint32_t ma1 = __byte_perm(ea, 0, 0x4441), ma2 = __byte_perm(ea, 0, 0x4442);       \
+            const uint32_t mb1 = __byte_perm(eb, 0, 0x4441), mb2 = __byte_perm(eb, 0, 0x4442);       \
+            VC2B_LANE_PAIR16(0, ma1, __mulhi((int)ea, 4), ma2, __mulhi((int)(ea << 24), 4))          \
+            VC2B_LANE_PAIR16(1, mb1, __mulhi((int)eb, 4), mb2, __mulhi((int)(eb << 24), 4))          \
+            maxmag = max(max(maxmag, max(ma1, ma2)), max(mb1, mb2));                                 \
+        } else {                                                                                     \
+            VC2B_LANE_STEP16(0, false)                                                               \
+            VC2B_LANE_STEP16(1, false)                                                               \
+            VC2B_LANE_STEP16(2, false)                                                               \
+            VC2B_LANE_STEP16(3, false)                                                               \
+            VC2B_LANE_SETTLE()                                                                       \
+        }                                                                                            \
+    }
+
     const int c = lane & 15, h = lane >> 4;   // store phase: half-warp h takes slice 2k+h, lane c its pair c
     for (int j0 = 0; j0 < ncodes; j0 += CH) {
         // ---- decode: lane = slice, CH codes each ---------------------------------------------------
+        lane_chunk_start(R);
         if (j0 + CH <= ncodes) {
+            if (j0 == next) VC2B_LANE_NEXT_BAND(0)
+            if (next - j0 >= CH) {  // one band covers the chunk (most chunks): no band tests inside
 #pragma unroll 1
-            for (int g = 0; g < CH / 4; g++) {
-                if (j0 == next) VC2B_LANE_NEXT_BAND(0)
-                if (next - j0 >= 4) {
-                    const uint32_t ea = lds_u32(plut_addr + (((uint32_t)(R.buf >> 32) >> (32 - kPairBits)) << 2));
-                    const uint32_t la = ea & 15u;
-                    const uint64_t bufa = R.buf << la;
-                    const uint32_t eb = lds_u32(plut_addr + (((uint32_t)(bufa >> 32) >> (32 - kPairBits)) << 2));
-                    const uint32_t lb = eb & 15u;
-                    if (__all_sync(0xffffffffu, qfast && la * lb != 0)) {
-                        R.buf = bufa << lb;
-                        R.avail -= (int)(la + lb);
-                        const uint32_t ma1 = __byte_perm(ea, 0, 0x4441), ma2 = __byte_perm(ea, 0, 0x4442);
-                        const uint32_t mb1 = __byte_perm(eb, 0, 0x4441), mb2 = __byte_perm(eb, 0, 0x4442);
-                        VC2B_LANE_PAIR16(0, ma1, __mulhi((int)ea, 4), ma2, __mulhi((int)(ea << 24), 4))
-                        VC2B_LANE_PAIR16(1, mb1, __mulhi((int)eb, 4), mb2, __mulhi((int)(eb << 24), 4))
-                        maxmag = max(max(maxmag, max(ma1, ma2)), max(mb1, mb2));
+                for (int g = 0; g < CH / 4; g++) {
+                    VC2B_LANE_QUAD16()
+                    lane_refill(R);
+                    j0 += 4;
+                    t16 += 2 * TS2;
+                }
+            } else {
+#pragma unroll 1
+                for (int g = 0; g < CH / 4; g++) {
+                    if (j0 == next) VC2B_LANE_NEXT_BAND(0)
+                    if (next - j0 >= 4) {
+                        VC2B_LANE_QUAD16()
                     } else {
                         VC2B_LANE_STEP16(0, false)
-                        VC2B_LANE_STEP16(1, false)
-                        VC2B_LANE_STEP16(2, false)
-                        VC2B_LANE_STEP16(3, false)
+                        VC2B_LANE_STEP16(1, true)
+                        VC2B_LANE_STEP16(2, true)
+                        VC2B_LANE_STEP16(3, true)
                         VC2B_LANE_SETTLE()
                     }
-                } else {
-                    VC2B_LANE_STEP16(0, false)
-                    VC2B_LANE_STEP16(1, true)
-                    VC2B_LANE_STEP16(2, true)
-                    VC2B_LANE_STEP16(3, true)
-                    VC2B_LANE_SETTLE()
+                    lane_refill(R);
+                    j0 += 4;
+                    t16 += 2 * TS2;
                 }
-                lane_refill(R);
-                j0 += 4;
-                t16 += 2 * TS2;
             }
             j0 -= CH;
             t16 -= (CH / 2) * TS2;
@@ -808,6 +844,7 @@ __device__ __forceinline__ void lanes_block16(const DevParams &P, const int comp
         __syncwarp();
     }
     VC2B_LANE_CLOSE_BAND()
+#undef VC2B_LANE_QUAD16
 #undef VC2B_LANE_STEP16
 #undef VC2B_LANE_PAIR16
 #undef VC2B_LANE_NEXT_BAND
@@ -867,7 +904,7 @@ __device__ __forceinline__ void build_lane_block(const DevParams &P, LaneBlock &
 
 // One LANE per slice; a warp task is 32 consecutive slices of one picture.
 template <bool LD, bool C16>
-__global__ void __launch_bounds__(kLaneWarps * 32, 2)
+__global__ void __launch_bounds__(kLaneWarps * 32, 1)
 unpack_lanes_kernel(DevParams P, const uint8_t *__restrict__ data, const int64_t *__restrict__ pic_offset,
                     int npictures, const uint32_t *__restrict__ slice_offset, int32_t *__restrict__ coeffs,
                     int16_t *__restrict__ coeffs16, int32_t *__restrict__ qindex_out, int32_t *__restrict__ status)
