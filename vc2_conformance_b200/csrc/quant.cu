@@ -811,6 +811,12 @@ pack_slices_kernel(DevParams P, FitArgs F, const int32_t *__restrict__ coeffs, i
   }  // slices of this warp
 }
 
+}  // namespace vc2b
+
+#include "pack_lanes.cuh"
+
+namespace vc2b {
+
 // ---------------------------------------------------------------------------
 // whole-picture quantize_coeffs (encoder/pictures.py:251): forward_quant of every coefficient at
 // max(qindex of its slice - quant matrix value, 0); output in the coefficient layout
@@ -1170,6 +1176,18 @@ static int launch_pack(const vc2b_params *p, const int32_t *d_coeffs, int npictu
     cudaStream_t s = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(d_out, 0, (size_t)out_stride * npictures, s);
     if (e != cudaSuccess) return (int)e;
+    if (pack_lanes_eligible(P)) {
+        // small slices that all have the same rectangles (every BASELINE configuration): one LANE per slice
+        const long long tasks = (long long)npictures * ((nslices + 31) / 32);
+        long long nblk = (tasks + kPkWarps - 1) / kPkWarps;
+        if (nblk > 148LL * 2) nblk = 148LL * 2;  // persistent: two CTAs of 16 warps per SM
+        e = cudaFuncSetAttribute(pack_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPkSmemBytes);
+        if (e != cudaSuccess) return (int)e;
+        pack_lanes_kernel<<<(unsigned)nblk, kPkWarps * 32, kPkSmemBytes, s>>>(
+            P, F, d_coeffs, npictures, d_qindex, d_slice_bits, d_out, out_stride);
+        VC2B_CHECK_LAUNCH();
+        return 0;
+    }
     const long long warps = npictures * nslices;
     long long nblk = (warps + kQWarps - 1) / kQWarps;
     if (nblk > 148LL * 16) nblk = 148LL * 16;  // persistent CTAs (the reference map is built once per CTA)
