@@ -95,8 +95,8 @@ int64_t vc2b_transform_scratch_bytes(const vc2b_params *p);
 /* HQ slice offsets: the dependent chain hidden in the sequential reader of
  * hq_slice (decoder/transform_data_syntax.py:212-251; each slice's start is known only after
  * the three length bytes of the previous one).
- *   d_data        transform-data bytes of all pictures, back to back; must be followed by at
- *                 least 16 readable padding bytes
+ *   d_data        transform-data bytes of all pictures, back to back; 16-byte aligned (the kernels read
+ *                 aligned 16-byte pieces) and followed by at least 16 readable padding bytes
  *   d_pic_offset  [npictures+1] int64: byte offset of each picture's transform data in d_data;
  *                 entry i+1 bounds picture i (reads past it are UnexpectedEndOfStream)
  *   d_slice_offset [npictures*slices] uint32 out: start of each slice relative to its picture

@@ -1040,6 +1040,7 @@ int vc2b_hq_slice_offsets(const vc2b_params *p, const uint8_t *d_data, const int
     if (st) return st;
     if (P.is_ld) return VC2B_E_BAD_PARAMS;
     if (npictures <= 0) return 0;
+    if (reinterpret_cast<uintptr_t>(d_data) & 15) return VC2B_E_BAD_PARAMS;  // aligned 16-byte loads
     hq_walk_kernel<<<npictures, kWalkThreads, 0, (cudaStream_t)stream>>>(P, d_data, d_pic_offset, npictures,
                                                                           d_slice_offset, d_status);
     VC2B_CHECK_LAUNCH();
@@ -1071,6 +1072,7 @@ static int unpack_impl(const vc2b_params *p, const uint8_t *d_data, const int64_
     if (npictures <= 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
     if (!P.is_ld && !d_slice_offset) return VC2B_E_BAD_PARAMS;
+    if (reinterpret_cast<uintptr_t>(d_data) & 15) return VC2B_E_BAD_PARAMS;  // the kernels stage aligned 16-byte pieces
     // Small slices (the production geometry): one LANE per slice.  Large slices: one WARP per slice.
     // vc2b_set_unpack_kernel overrides the choice (tests exercise both kernels on the same streams).
     bool lanes = lanes_eligible(P);
