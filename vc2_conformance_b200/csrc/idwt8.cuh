@@ -441,15 +441,20 @@ static int launch_wide_steps(LevelArgs A, int npic, cudaStream_t s)
     }
     dim3 grid(maxtiles, A.ncomp, npic);
     const int mode = (A.hb16 ? kModeHb16 : 0) | (A.ll16 ? kModeLl16 : 0) | (A.out16 ? kModeOut16 : 0);
-    switch (mode) {
-    case 0: idwt_stream8_kernel<FV, FH, STEPS, 0><<<grid, 32, 0, s>>>(A); break;
-    case kModeHb16: idwt_stream8_kernel<FV, FH, STEPS, kModeHb16><<<grid, 32, 0, s>>>(A); break;
-    case kModeHb16 | kModeLl16: idwt_stream8_kernel<FV, FH, STEPS, kModeHb16 | kModeLl16><<<grid, 32, 0, s>>>(A); break;
-    case kModeHb16 | kModeOut16: idwt_stream8_kernel<FV, FH, STEPS, kModeHb16 | kModeOut16><<<grid, 32, 0, s>>>(A); break;
-    case kModeHb16 | kModeLl16 | kModeOut16:
-        idwt_stream8_kernel<FV, FH, STEPS, kModeHb16 | kModeLl16 | kModeOut16><<<grid, 32, 0, s>>>(A);
-        break;
-    default: return VC2B_E_UNSUPPORTED;
+    if (mode == 0) {
+        idwt_stream8_kernel<FV, FH, STEPS, 0><<<grid, 32, 0, s>>>(A);
+    } else if constexpr (FV == FH) {  // the int16 planes need one filter for both directions (coeff16_transform_ok)
+        switch (mode) {
+        case kModeHb16: idwt_stream8_kernel<FV, FH, STEPS, kModeHb16><<<grid, 32, 0, s>>>(A); break;
+        case kModeHb16 | kModeLl16: idwt_stream8_kernel<FV, FH, STEPS, kModeHb16 | kModeLl16><<<grid, 32, 0, s>>>(A); break;
+        case kModeHb16 | kModeOut16: idwt_stream8_kernel<FV, FH, STEPS, kModeHb16 | kModeOut16><<<grid, 32, 0, s>>>(A); break;
+        case kModeHb16 | kModeLl16 | kModeOut16:
+            idwt_stream8_kernel<FV, FH, STEPS, kModeHb16 | kModeLl16 | kModeOut16><<<grid, 32, 0, s>>>(A);
+            break;
+        default: return VC2B_E_UNSUPPORTED;
+        }
+    } else {
+        return VC2B_E_UNSUPPORTED;
     }
     VC2B_CHECK_LAUNCH();
     return 0;
