@@ -805,7 +805,57 @@ __device__ __forceinline__ void lanes_block16(const DevParams &P, const int comp
         }
         __syncwarp();
 
-        // ---- store: two slices per instruction, 16 pairs of consecutive codes each --------------------
+        // ---- store ---------------------------------------------------------------------------------------
+        if constexpr (INTERLEAVED) {
+            // C1 and C2 alternate: tile word p holds (C1[jj], C2[jj]).  A lane takes words 2q and 2q + 1 of a slice
+            // -- two adjacent coefficients of each plane -- and writes one 32-bit pair per plane; an instruction
+            // covers four slices (lane = q + 8 r, slice 4 k + r), conflict-free on the tile.
+            const int q = lane & 7, r = lane >> 3;
+            const int jj = (j0 >> 1) + 2 * q;           // first of the lane's two coefficients
+            const int ncoef = ncodes >> 1;
+            if (jj < ncoef) {
+                const bool two = jj + 1 < ncoef;
+                const uint32_t loc0 = S.map[mc][jj];
+                const uint32_t loc1 = two ? S.map[mc][jj + 1] : loc0;
+                const int mb0 = loc0 >> 26, off0 = loc0 & 0x3ffffffu;
+                const int mb1 = loc1 >> 26, off1 = loc1 & 0x3ffffffu;
+                const uint32_t *tb = reinterpret_cast<const uint32_t *>(&W.tile[(2 * q) * kLaneTS + r]);
+                const bool wide = two && mb0 == mb1 && mb0 != 0 && off1 == off0 + 1 && !(off0 & 1) && S.even16[mc][mb0];
+                if (wide) {
+                    char *p1 = reinterpret_cast<char *>(o16 + off0), *p2 = reinterpret_cast<char *>(o16b + off0);
+                    const int32_t *bb = &W.base[r * kLaneBaseStride + mb0];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        if (act_mask == 0xffffffffu || ((act_mask >> (4 * k + r)) & 1)) {
+                            const uint32_t w0 = tb[4 * k], w1 = tb[kLaneTS + 4 * k];
+                            const unsigned long long at = 2ull * (uint32_t)bb[4 * k * kLaneBaseStride];
+                            *reinterpret_cast<uint32_t *>(p1 + at) = __byte_perm(w0, w1, 0x5410);
+                            *reinterpret_cast<uint32_t *>(p2 + at) = __byte_perm(w0, w1, 0x7632);
+                        }
+                    }
+                } else {
+#pragma unroll 2
+                    for (int k = 0; k < 8; k++) {
+                        const int s = 4 * k + r;
+                        if (!((act_mask >> s) & 1)) continue;
+                        const uint32_t w0 = tb[4 * k], w1 = tb[kLaneTS + 4 * k];
+                        if (mb0 != 0) {
+                            const int at = W.base[s * kLaneBaseStride + mb0] + off0;
+                            o16[at] = (int16_t)(w0 & 0xffffu);
+                            o16b[at] = (int16_t)(w0 >> 16);
+                        }
+                        if (two && mb1 != 0) {
+                            const int at = W.base[s * kLaneBaseStride + mb1] + off1;
+                            o16[at] = (int16_t)(w1 & 0xffffu);
+                            o16b[at] = (int16_t)(w1 >> 16);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            continue;
+        }
+        // two slices per instruction, 16 pairs of consecutive codes each
         const int j = j0 + 2 * c;
         if (j < ncodes) {
             const bool two = j + 1 < ncodes;
