@@ -314,6 +314,47 @@ def test_coeff16_plane(case, group):
             assert (planes[c] == decoded[i][c]).all(), (case, "picture", i, c)
 
 
+COEFF16_EXTRA = [
+    # LD (interleaved chroma block, DC prediction on the int32 level-0 band), several slice sizes
+    dict(luma_width=960, luma_height=272, color_diff_width=480, color_diff_height=272, luma_depth=10, wavelet_index=4,
+         dwt_depth=2, slices_x=30, slices_y=34, is_ld=1, slice_bytes_numerator=30 * 34 * 90 + 11,
+         slice_bytes_denominator=30 * 34),
+    dict(luma_width=512, luma_height=256, color_diff_width=512, color_diff_height=256, luma_depth=12, wavelet_index=1,
+         dwt_depth=3, slices_x=16, slices_y=16, is_ld=1, slice_bytes_numerator=16 * 16 * 400 + 3,
+         slice_bytes_denominator=16 * 16),
+    # HQ with slice prefix bytes and a slice_size_scaler above 1
+    dict(luma_width=512, luma_height=256, color_diff_width=256, color_diff_height=256, luma_depth=10, wavelet_index=0,
+         dwt_depth=3, slices_x=16, slices_y=32, slice_prefix_bytes=3, slice_size_scaler=4),
+]
+
+
+@pytest.mark.parametrize("kw", COEFF16_EXTRA)
+def test_coeff16_plane_ld_and_prefix(kw):
+    """The int16 coefficient plane on LD pictures and on HQ pictures with prefix bytes / a scaler: coefficients and
+    pictures equal the oracle's, and the int16 kernels are the ones that ran."""
+    import oracle as O
+    from vc2_conformance_b200.device import BatchCodec
+
+    p = _mk(**kw)
+    po = synth.oracle_params(p)
+    S = p.luma_width * p.luma_height + 2 * p.color_diff_width * p.color_diff_height
+    pics = [synth.noise_picture(p, 60), synth.ramp_picture(p, 61), synth.noise_picture(p, 62)]
+    streams, decoded = _oracle_streams(p, pics, [S // 2, S // 3, S // 4])
+    codec = BatchCodec(p, len(pics), coeff16=True)
+    assert codec.coeff16
+    host, offs = codec.pack_host_streams(streams)
+    codec.decode_host(host, offs, len(pics))
+    st = codec.status_host(len(pics))
+    assert (st[:, 0] == 0).all(), st   # nothing was redone through the int32 planes
+    for i in range(len(pics)):
+        comps = O.transform_data(po, streams[i])[1]
+        got = codec.coeff_components(i)
+        planes = codec.picture_planes(i)
+        for c in range(3):
+            assert (got[c] == np.asarray(comps[c]).reshape(-1)).all(), ("coefficients", i, c)
+            assert (planes[c] == decoded[i][c]).all(), ("picture", i, c)
+
+
 def test_coeff16_overflow_is_redone_through_the_int32_plane():
     """A lossless 16-bit noise picture has high-pass coefficients beyond int16 (flagged by the unpack), a 16-bit
     ramp has intermediate low-pass bands beyond int16 (flagged by the IDWT level that produces them): both come
