@@ -469,8 +469,10 @@ static void plan_scratch(const DevParams &P, int c0, int c1, ScratchPlan *sp)
         }
         sp->comp_off_a[c] = sp->size_a;
         sp->comp_off_b[c] = sp->size_b;
-        sp->size_a += (a + 3) & ~3LL;  // keep every region 16-byte aligned (paired stores)
-        sp->size_b += (b + 3) & ~3LL;
+        // every region a multiple of 8 elements: 16-byte aligned vector stores for int32 and for int16 bands
+        // (vc2b_idwt16), whatever the picture's position in the group
+        sp->size_a += (a + 7) & ~7LL;
+        sp->size_b += (b + 7) & ~7LL;
     }
 }
 
