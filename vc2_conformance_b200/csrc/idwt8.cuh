@@ -467,7 +467,7 @@ static int launch_wide(const LevelArgs &A, int npic, cudaStream_t s)
     // pipeline drain: 14 of them for Fidelity, 4 for LeGall).  Estimated duration of the launch with
     // strip height S: (waves of resident warps, at least one, plus half a wave of tail) x S steps;
     // short strips win only while the launch is a few waves and their RSP / STEPS is still decent.
-    const double slots = 148.0 * 14;
+    const double slots = 148.0 * (A.hb16 ? 16 : 14);  // resident warps (the int16 modes are compiled for 16 per SM)
     double best = 0;
     int pick = 64;
     const int rsp[3] = {Strip8Cfg<FV, FH, 64>::RSP, Strip8Cfg<FV, FH, 32>::RSP, Strip8Cfg<FV, FH, 16>::RSP};
