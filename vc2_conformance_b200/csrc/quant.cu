@@ -338,6 +338,7 @@ struct FitArgs {
     int max_qm;
     int stage_cap;                // coefficients the per-warp staging area holds (quantize_fit_kernel)
     int use_map;                  // every band fits the 24-bit offsets of FitMap
+    int uniform;                  // every band divides evenly between the slices: all slices have the same rectangles
     int fixed_qindex;             // >= 0: no search, only the block sizes at this index (vc2b_slice_bits)
     const int32_t *fixed_per_slice;  // != nullptr: no search, block sizes at the slice's own index
     const uint32_t *lossless_offset; // packer, make_transform_data_hq_lossless (:528): [npictures * (slices + 1)]
@@ -476,24 +477,74 @@ quantize_fit_kernel(DevParams P, FitArgs F, const int32_t *__restrict__ coeffs, 
   const long long nwarps_total = (long long)gridDim.x * kQWarps;
   const long long run = (total_slices + nwarps_total - 1) / nwarps_total;
   const long long gw0 = ((long long)blockIdx.x * kQWarps + warp) * run;
+  SliceBands &TY = tabs[warp][0];
+  SliceBands &TC = tabs[warp][1];
+  // Uniform geometry (every BASELINE configuration): the slice tables are the same for every slice but for the
+  // corners of the rectangles, and slice number, position and budget advance by additions -- the divisions of
+  // build_slice_bands, gw / nslices and slice_bytes were a third of this kernel's instructions.
+  const bool uni = F.uniform != 0;
+  int u_ny = 0, u_nc = 0, rw_y = 0, rh_y = 0, rw_c = 0, rh_c = 0;
+  if (uni) {
+      __syncwarp();
+      u_ny = build_slice_bands(P, 0, 0, 0, TY, lane);
+      u_nc = build_slice_bands(P, 1, 0, 0, TC, lane);
+      if (lane < P.nb) {
+          rw_y = P.band[0][lane].w / P.slices_x;
+          rh_y = P.band[0][lane].h / P.slices_y;
+          rw_c = P.band[1][lane].w / P.slices_x;
+          rh_c = P.band[1][lane].h / P.slices_y;
+      }
+  }
+  // running slice position and budget: floor((n+1) T / D) - floor(n T / D) = floor((n T mod D + T) / D)
+  const unsigned long long bud_t = P.is_ld ? (unsigned long long)P.sb_num : (unsigned long long)F.total_coeff_bytes;
+  const unsigned long long bud_d = P.is_ld ? (unsigned long long)P.sb_den
+                                           : (unsigned long long)nslices * (unsigned long long)P.slice_size_scaler;
+  int cur_pic = (int)(gw0 / nslices);
+  int cur_n = (int)(gw0 - (long long)cur_pic * nslices);
+  int cur_sy = cur_n / P.slices_x, cur_sx = cur_n - cur_sy * P.slices_x;
+  unsigned long long bud_rem = uni ? ((unsigned long long)cur_n * bud_t) % bud_d : 0ull;
   for (long long gw = gw0; gw < min(gw0 + run, total_slices); gw++) {
-    const int pic = (int)(gw / nslices);
+    int pic, n, sy, sx;
+    if (uni) {
+        pic = cur_pic; n = cur_n; sy = cur_sy; sx = cur_sx;
+    } else {
+        pic = (int)(gw / nslices);
+        n = (int)(gw - (long long)pic * nslices);
+        sy = n / P.slices_x;
+        sx = n - sy * P.slices_x;
+    }
     // issued before the staging loads so that its latency hides behind them
     const int shared_hint = own_hint < 0 ? g_qindex_hint[pic & (kHintSlots - 1)] : 0;
-    const int n = (int)(gw - (long long)pic * nslices);
-    const int sy = n / P.slices_x, sx = n - sy * P.slices_x;
     const int32_t *pc = coeffs + (size_t)pic * P.pic_coeffs;
-    SliceBands &TY = tabs[warp][0];
-    SliceBands &TC = tabs[warp][1];
     const SliceStage S = slice_stage_at(stage_mem, warp, F.stage_cap);
     __syncwarp();
-    const int ny = build_slice_bands(P, 0, sx, sy, TY, lane);
-    const int nc = build_slice_bands(P, 1, sx, sy, TC, lane);
+    int ny, nc;
+    long long uni_len = 0;   // hq_total_length / slice_bytes of this slice
+    if (uni) {
+        if (lane < P.nb) {
+            TY.base[lane] = P.band[0][lane].off + (rh_y * sy) * P.band[0][lane].w + rw_y * sx;
+            TC.base[lane] = P.band[1][lane].off + (rh_c * sy) * P.band[1][lane].w + rw_c * sx;
+        }
+        __syncwarp();
+        ny = u_ny;
+        nc = u_nc;
+        const unsigned long long ssum = bud_rem + bud_t;
+        const unsigned long long dq = (ssum >> 32) == 0 && (bud_d >> 32) == 0 ? (unsigned long long)((uint32_t)ssum / (uint32_t)bud_d)
+                                                                           : ssum / bud_d;
+        uni_len = (long long)dq;
+        bud_rem = ssum - dq * bud_d;
+        // the next slice of the run
+        if (++cur_sx == P.slices_x) { cur_sx = 0; cur_sy++; }
+        if (++cur_n == nslices) { cur_n = 0; cur_sx = 0; cur_sy = 0; cur_pic++; bud_rem = 0; }
+    } else {
+        ny = build_slice_bands(P, 0, sx, sy, TY, lane);
+        nc = build_slice_bands(P, 1, sx, sy, TC, lane);
+    }
     // fast path: slice staged as 4|c| in shared memory, every magnitude below kFastMagLimit
     bool staged = (ny + 2 * nc) <= F.stage_cap;
     if (staged) {
         uint32_t mx;
-        if (matches_fit_map(P, M, TY, TC, lane)) {
+        if (uni ? (M.ok != 0) : matches_fit_map(P, M, TY, TC, lane)) {
             const int32_t *c0 = pc + P.comp_off[0], *c1 = pc + P.comp_off[1], *c2 = pc + P.comp_off[2];
             mx = stage_mapped<1>(M.e, TY, c0, nullptr, ny, S.coef, S.band, nullptr, nullptr, 1, lane);
             if (P.is_ld)
@@ -512,13 +563,13 @@ quantize_fit_kernel(DevParams P, FitArgs F, const int32_t *__restrict__ coeffs, 
 
     long long target, align;
     if (P.is_ld) {
-        const long long sb = ld_slice_offset(P, n + 1) - ld_slice_offset(P, n);
+        const long long sb = uni ? uni_len : ld_slice_offset(P, n + 1) - ld_slice_offset(P, n);
         target = 8 * sb - 7;
         target -= ilog2_ceil(target);
         align = 1;
     } else {
         align = 8LL * P.slice_size_scaler;
-        target = align * hq_total_length(P, F, n);
+        target = align * (uni ? uni_len : hq_total_length(P, F, n));
     }
     const int ialign = (int)align;
 
@@ -1040,9 +1091,15 @@ static int launch_fit(const vc2b_params *p, const int32_t *d_coeffs, int npictur
                    ((P.band[c][b].h + P.slices_y - 1) / P.slices_y);
     F.stage_cap = cap <= kStageMax ? (int)((cap + 15) & ~15LL) : 16;  // larger slices are searched unstaged
     F.use_map = 1;
+    F.uniform = 1;
     for (int c = 0; c < 3; c++)
-        for (int b = 0; b < P.nb; b++)
+        for (int b = 0; b < P.nb; b++) {
             if ((long long)P.band[c][b].w * P.band[c][b].h >= (1 << 24)) F.use_map = 0;
+            if (P.band[c][b].w % P.slices_x || P.band[c][b].h % P.slices_y || P.band[c][b].w < P.slices_x ||
+                P.band[c][b].h < P.slices_y)
+                F.uniform = 0;
+        }
+    if (F.total_coeff_bytes < 0 || (P.is_ld && (P.sb_num < 0 || P.sb_den <= 0))) F.uniform = 0;
     const size_t smem = kQWarps * slice_stage_bytes(F.stage_cap);
     {   // static + dynamic shared memory can exceed the 48 KB default for the largest staged slices;
         // the attribute is per device, so it is set on every call (cheap) rather than once per process
