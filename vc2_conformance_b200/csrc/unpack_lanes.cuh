@@ -6,18 +6,21 @@
 // SMALL slices (<= kLaneMaxCoef coefficients per slice component).
 //
 // Design (B200): exp-Golomb decoding is a dependent chain per bounded block, but the blocks of
-// different slices are independent, so here every LANE owns a slice and walks its own bit string:
-// a 64-bit bit buffer in registers, an 8-bit window LUT that yields length, magnitude and sign of
-// every code of up to 8 bits in one shared-memory lookup, refills predicated every fourth
-// coefficient.  A warp therefore decodes 32 slices in lockstep at ~1 instruction per coefficient
-// and lane instead of the ~4 warp instructions per coefficient of the scan-based warp-per-slice
-// scheme.  The dequantised values go through a padded 16x34 shared-memory tile (written
-// [coefficient][slice], read [slice][coefficient], both conflict-free) so that the stores to the
-// subband rectangles are issued per slice pair with consecutive lanes on consecutive coefficients --
-// the same coalescing as the warp-per-slice kernel, and every coefficient is written exactly once
-// (no zero-fill pass).  The coefficient -> (band, y, x) map is built once per CTA for the dimensions
-// of slice (0, 0); slices of ragged geometries whose rectangles differ take a slower path that
-// locates each coefficient from the slice's own band table.
+// different slices are independent, so here every LANE owns a slice and walks its own bit string, the 32 lanes
+// of a warp in lockstep on the code position:
+//   * a 64-bit bit buffer in registers, refilled every fourth code from a lane-private shared-memory FIFO that
+//     cp.async tops up once per chunk of codes (LaneReader);
+//   * TWO codes per look-up: a 12-bit window table (build_pair_lut) yields both magnitudes, both signs and the
+//     bits consumed; a group of four codes in which some lane's pair does not fit the window falls back, for
+//     the whole warp, to the one-code step (8-bit window table, long codes out of line);
+//   * the dequantised values go through a padded shared-memory tile (written [code][slice], read
+//     [slice][code], both conflict-free) so that the stores to the subband rectangles are issued per slice
+//     pair with consecutive lanes on consecutive coefficients, every coefficient written exactly once;
+//   * lanes_block writes the int32 plane; lanes_block16 the int16 plane of vc2b_unpack16 (two codes per tile
+//     word, 32-bit pair stores, level-0 band straight to the int32 plane, overflow flag).
+// The coefficient -> (band, y, x) map is built once per CTA for the dimensions of slice (0, 0); slices of
+// ragged geometries whose rectangles differ take a slower path (lanes_block only) that locates each
+// coefficient from the slice's own band table.  0.92 warp instructions per coefficient at cfg2.
 #pragma once
 
 namespace vc2b {
