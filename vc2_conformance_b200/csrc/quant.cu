@@ -611,37 +611,59 @@ quantize_fit_kernel(DevParams P, FitArgs F, const int32_t *__restrict__ coeffs, 
     // so the reference's linear search (quantize_to_fit :329) equals this bisection.
     int lo = F.minimum_qindex;
     int hi = max(lo, 128 + F.max_qm + 4);  // everything quantises to zero here (int32 envelope)
+    // Neighbouring slices of a picture usually need almost the same index: gallop outwards from the last
+    // answer (a hint only -- every bound used below is established by an actual probe), then bisect the
+    // bracket, then fetch the block sizes at the answer unless the last probe that fitted was the answer.
+    // One loop with ONE probe site: with the probe inlined at every step of the gallops and the bisection the
+    // kernel spent a stall_no_instruction per issue waiting for its own code (ncu, r2_v11).
+    enum { kHint = 0, kDown = 1, kUp = 2, kBisect = 3, kSizes = 4 };
+    const bool searching = !(F.fixed_qindex >= 0 || F.fixed_per_slice) && target >= 0;
+    int phase = kSizes;
+    const int hint = own_hint < 0 ? shared_hint : own_hint;
     if (F.fixed_qindex >= 0 || F.fixed_per_slice) {
         lo = hi = F.fixed_per_slice ? F.fixed_per_slice[gw] : F.fixed_qindex;  // sizes only, no search
     } else if (target < 0) {
         lo = hi;  // cannot fit: reported as the saturated index (the reference would not terminate)
     } else {
-        // Neighbouring slices of a picture usually need almost the same index: gallop outwards from
-        // the last answer any warp published for this picture (a hint only -- every bound used
-        // below is established by an actual probe), then bisect the bracket.
-        const int hint = own_hint < 0 ? shared_hint : own_hint;
-        if (hint > lo && hint < hi) {
-            if (fits(hint)) {
-                hi = hint;
-                for (int step = 1; hi - step > lo; step *= 2) {
-                    if (fits(hi - step)) hi -= step; else { lo = hi - step + 1; break; }
-                }
-            } else {
-                lo = hint + 1;
-                for (int step = 1; lo + step < hi; step *= 2) {
-                    if (!fits(lo + step - 1)) lo += step; else { hi = lo + step - 1; break; }
-                }
-            }
+        phase = (hint > lo && hint < hi) ? kHint : kBisect;
+    }
+    int step = 1;
+#pragma unroll 1
+    while (true) {
+        int q;
+        if (phase == kHint) {
+            q = hint;
+        } else if (phase == kDown) {
+            if (!(hi - step > lo)) { phase = kBisect; continue; }
+            q = hi - step;
+        } else if (phase == kUp) {
+            if (!(lo + step < hi)) { phase = kBisect; continue; }
+            q = lo + step - 1;
+        } else if (phase == kBisect) {
+            if (!(lo < hi)) { phase = kSizes; continue; }
+            q = (lo + hi) >> 1;
+        } else {
+            if (ok_q == lo) { by = oy; bc1 = o1; bc2 = o2; break; }  // the answer is the last probe that fitted
+            q = lo;
         }
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (fits(mid)) hi = mid; else lo = mid + 1;
+        const bool ok = fits(q);
+        if (phase == kHint) {
+            if (ok) { hi = hint; phase = kDown; } else { lo = hint + 1; phase = kUp; }
+            step = 1;
+        } else if (phase == kDown) {
+            if (ok) { hi -= step; step *= 2; } else { lo = hi - step + 1; phase = kBisect; }
+        } else if (phase == kUp) {
+            if (!ok) { lo += step; step *= 2; } else { hi = lo + step - 1; phase = kBisect; }
+        } else if (phase == kBisect) {
+            if (ok) hi = q; else lo = q + 1;
+        } else {
+            break;  // block sizes at the answer
         }
+    }
+    if (searching) {
         if (lane == 0 && own_hint < 0) g_qindex_hint[pic & (kHintSlots - 1)] = lo;
         own_hint = lo;
     }
-    if (ok_q == lo) { by = oy; bc1 = o1; bc2 = o2; }  // the answer is the last probe that fitted
-    else fits(lo);
     if (lane == 0) {
         qindex_out[gw] = lo;
         if (bits_out) {
