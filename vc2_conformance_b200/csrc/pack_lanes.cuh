@@ -206,7 +206,7 @@ __device__ __forceinline__ void pk_block(const DevParams &P, const int comp, PkW
                 rec = t.y;
             }
             const int32_t cv = Wp.tile[i * kPkTS + lane];
-            const uint32_t m = cv < 0 ? (uint32_t)(-(long long)cv) : (uint32_t)cv;
+            const uint32_t m = (uint32_t)abs(cv);   // one IABS; |INT_MIN| stays 2^31 as an unsigned value
             const uint32_t r = pk_quant(m, qf, rec);
             if (active) pk_code(W, S, cv < 0 ? -(int32_t)r : (int32_t)r, left);
         }
